@@ -1,0 +1,214 @@
+/*
+ * xenodon_b200.h -- C ABI of the B200-native volume ray-traversal path.
+ *
+ * This is the drop-in boundary for the hot path of Snektron/Xenodon: everything the
+ * reference does between "a volume and a camera are known on the host" and "RGBA8
+ * pixels / per-frame timings are back on the host".  Each entry point names the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain C types only; no C++ or torch types cross the boundary;
+ *   - every function returns 0 on success and a negative xn_status on failure; the
+ *     message of the last failure on the calling thread is xn_last_error();
+ *   - a context (xn_ctx) is bound to one CUDA device and owns one stream; calls on
+ *     one context must come from one thread at a time (the reference is
+ *     single-threaded, src/main_loop.cpp:230-258); different contexts are independent;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     XN_ERR_CUDA.
+ *
+ * Reference-side binding: see INTEGRATION.md.
+ */
+#ifndef XENODON_B200_H
+#define XENODON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XN_API __attribute__((visibility("default")))
+
+typedef enum xn_status {
+    XN_OK = 0,
+    XN_ERR_INVALID = -1, /* bad argument / call order */
+    XN_ERR_CUDA = -2,    /* CUDA runtime failure (no device, OOM, launch error) */
+    XN_ERR_IO = -3,      /* file could not be opened / read / written */
+    XN_ERR_FORMAT = -4,  /* malformed TIFF / SVO / config / camera file */
+    XN_ERR_LIMIT = -5    /* exceeds a format or device limit */
+} xn_status;
+
+/* Traversal ids in the order of SHADER_OPTIONS, src/main_loop.cpp:37-43.
+ * Names accepted by xn_traversal_from_name are the reference's --shader values. */
+typedef enum xn_traversal {
+    XN_DDA = 0,       /* resources/dda.comp        "dda"       (grid volumes) */
+    XN_SVO_NAIVE = 1, /* resources/svo_naive.comp  "svo-naive" (octree volumes) */
+    XN_ESVO = 2,      /* resources/esvo.comp       "esvo" */
+    XN_SVO_DF = 3,    /* resources/svo_df.comp     "svo-df" */
+    XN_SVO_ROPE = 4   /* resources/svo_rope.comp   "svo-rope" (needs a --rope file) */
+} xn_traversal;
+
+/* src/model/Octree.h:35-45 / resources/octree.glsl:6-10: the on-disk and host node. */
+typedef struct xn_node {
+    uint32_t children[8];
+    uint32_t color;         /* r | g<<8 | b<<16 | a<<24 */
+    uint32_t is_leaf_depth; /* bit 31 = leaf, low 31 bits = depth */
+} xn_node;
+
+/* vk::Rect2D as used by Output::region(), src/backend/Output.h:17 */
+typedef struct xn_rect {
+    int32_t x, y;
+    uint32_t w, h;
+} xn_rect;
+
+/* RenderStats, src/render/RenderStats.h:14-27 (one frame, one or more devices) */
+typedef struct xn_render_stats {
+    uint64_t total_rays;
+    uint64_t outputs;
+    double total_render_time; /* ms, summed over outputs */
+    double max_render_time;   /* ms */
+    double min_render_time;   /* ms */
+} xn_render_stats;
+
+typedef struct xn_ctx xn_ctx;
+
+XN_API const char* xn_last_error(void);
+XN_API const char* xn_version(void);
+XN_API int xn_traversal_from_name(const char* shader_name); /* <0 if unknown */
+XN_API const char* xn_traversal_name(int traversal);
+
+/* ---- devices: Instance::physical_devices / `xenodon sysinfo` (src/sysinfo.cpp) ---- */
+XN_API int xn_device_count(int* count);
+XN_API int xn_device_name(int device, char* buf, size_t cap);
+
+/* ---- context: HeadlessOutput ctor (device, queues, fence, offscreen image),
+ *      src/backend/headless/HeadlessOutput.cpp:38-63 ---- */
+XN_API int xn_ctx_create(int cuda_device, xn_ctx** out);
+XN_API int xn_ctx_destroy(xn_ctx* ctx);
+XN_API int xn_ctx_device(const xn_ctx* ctx);
+
+/* ---- volume upload (once per device; the volume is replicated per device) ----
+ * xn_upload_grid replaces DdaRaytraceResources (src/render/DdaRaytraceAlgorithm.cpp:15-97):
+ *   rgba = nx*ny*nz RGBA8 voxels, index x + y*nx + z*nx*ny (src/model/Grid.h:50-52).
+ *   Sizes are 64-bit: grids beyond Vulkan's 4 GB binding limit are accepted.
+ * xn_upload_svo replaces SvoRaytraceResources (src/render/SvoRaytraceAlgorithm.cpp:12-48):
+ *   nodes = count 40-byte nodes exactly as stored in a .svo file, node 0 = root.
+ * The caller keeps ownership of the host arrays and may free them after return. */
+XN_API int xn_upload_grid(xn_ctx* ctx, const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz);
+XN_API int xn_upload_svo(xn_ctx* ctx, const xn_node* nodes, uint64_t count, uint64_t side);
+/* same, from memory already resident on ctx's device (copied device-to-device) */
+XN_API int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t ny, uint64_t nz);
+XN_API int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uint64_t side);
+/* deterministic synthetic volumes generated directly in device memory
+ * (BASELINE.md section 4): kind 0 = "bunny-CT", 1 = "TNG gas"; bound as the grid */
+XN_API int xn_synth_grid_device(xn_ctx* ctx, int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t seed);
+/* host generator producing bit-identical voxels (host memory, multi-threaded) */
+XN_API int xn_synth_grid_host(int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t seed, uint8_t* rgba_out);
+/* copy the bound grid back to the host (nx*ny*nz*4 bytes) */
+XN_API int xn_download_grid(xn_ctx* ctx, uint8_t* rgba_out, uint64_t cap_bytes);
+
+/* ---- per-output uniforms: Renderer::upload_uniform_buffers, src/render/Renderer.cpp:236-268 ----
+ * output  = this device's region (HeadlessConfig device{offset,extent});
+ * display = union of all regions (RenderContext::calculate_display_rect,
+ *           src/render/RenderContext.cpp:43-60), used for uv so tiles are seamless. */
+XN_API int xn_set_target(xn_ctx* ctx, const xn_rect* output, const xn_rect* display);
+/* ShaderParameters, src/render/RenderContext.h:16-20 / src/main_loop.cpp:197-201.
+ * model_dim = grid dimensions for tiff volumes, side^3 for svo volumes. */
+XN_API int xn_set_params(xn_ctx* ctx, const float voxel_ratio[3], const uint32_t model_dim[3],
+                         float emission_coeff);
+/* Redirect the render target: pixels of this context's region are stored at
+ * device_ptr[y * stride_px + x] (x, y relative to the region).  device_ptr may be
+ * memory of a PEER device (NVLink): the traversal kernel then stores finished pixels
+ * straight into the gathering device's frame, fusing the tile gather into the kernel.
+ * NULL restores the context's own offscreen target. */
+XN_API int xn_set_target_buffer(xn_ctx* ctx, void* device_ptr, size_t stride_px);
+
+/* ---- one frame: Renderer::render, src/render/Renderer.cpp:55-103 ----
+ * Asynchronous: enqueues the traversal kernel bracketed by two timing events
+ * (RenderStatsCollector::pre/post_dispatch, src/render/RenderStats.cpp:46-57).
+ * translation is in user units; the library divides it by voxel_ratio exactly as
+ * Renderer.cpp:62 does. */
+XN_API int xn_render(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                     const float translation[3]);
+/* fence wait + RenderStatsCollector::collect (HeadlessOutput::synchronize,
+ * src/backend/headless/HeadlessOutput.cpp:90-93; src/render/RenderStats.cpp:59-83).
+ * kernel_ms (nullable) receives the device time of the last xn_render. */
+XN_API int xn_sync(xn_ctx* ctx, double* kernel_ms);
+/* HeadlessOutput::download, src/backend/headless/HeadlessOutput.cpp:95-136:
+ * copies the region's pixels to dst[y * stride_px + x]; stride_px 0 = region width. */
+XN_API int xn_download(xn_ctx* ctx, uint32_t* dst, size_t stride_px);
+
+/* Instrumented frame (not timed): per-ray trace() loop iterations and algorithmic
+ * bytes (4 B per texel fetch / node-field read as the shader source writes them).
+ * steps_out / bytes_out are host arrays of region w*h elements (nullable);
+ * totals_out[0] = sum of steps, totals_out[1] = sum of bytes (nullable). */
+XN_API int xn_render_stats_pass(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                                const float translation[3], uint32_t* steps_out, uint64_t* bytes_out,
+                                uint64_t totals_out[2]);
+
+/* ---- multi-device frame assembly: HeadlessDisplay::save's composite,
+ *      src/backend/headless/HeadlessDisplay.cpp:59-76 ----
+ * Gathers every context's tile into the enclosing rectangle of all regions on
+ * ctxs[0]'s device (peer-to-peer copies over NVLink when available), then copies the
+ * frame to host_dst (enclosing w*h pixels; pixels outside every region are
+ * 0xFF000000).  All contexts must be synchronized (xn_sync) first. */
+XN_API int xn_frame_gather(xn_ctx* const* ctxs, int n, uint32_t* host_dst, xn_rect* enclosing_out);
+
+/* Inter-process variant (one process per GPU): export ctx's frame buffer so peers can
+ * store into it.  handle_out receives 64 opaque bytes (cudaIpcMemHandle_t). */
+XN_API int xn_frame_buffer_create(xn_ctx* ctx, uint32_t w, uint32_t h, void** device_ptr_out,
+                                  uint8_t handle_out[64]);
+XN_API int xn_frame_buffer_open(xn_ctx* ctx, const uint8_t handle[64], void** device_ptr_out);
+XN_API int xn_frame_buffer_close(xn_ctx* ctx, void* device_ptr);
+XN_API int xn_frame_buffer_read(xn_ctx* ctx, const void* device_ptr, uint32_t w, uint32_t h,
+                                uint32_t* host_dst);
+
+/* ---- host-side data formats (API surface of the path) ---- */
+
+/* Grid::load_tiff, src/model/Grid.cpp:27-79 (multi-directory TIFF / BigTIFF -> RGBA8 grid,
+ * TIFFReadRGBAImage conventions: bottom-up rows, alpha pre-multiplied). */
+XN_API int xn_tiff_info(const char* path, uint64_t dims_out[3]);
+XN_API int xn_tiff_read(const char* path, uint8_t* rgba_out, uint64_t cap_bytes);
+/* writer used to make inputs (uncompressed contiguous RGBA, one directory per z) */
+XN_API int xn_tiff_write(const char* path, const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz,
+                         int bigtiff);
+
+/* Octree::load_svo / save_svo, src/model/Octree.cpp:50-114 */
+XN_API int xn_svo_info(const char* path, uint64_t* side_out, uint64_t* count_out);
+XN_API int xn_svo_read(const char* path, xn_node* nodes_out, uint64_t cap_nodes);
+XN_API int xn_svo_write(const char* path, const xn_node* nodes, uint64_t count, uint64_t side);
+
+/* build_octree, src/model/OctreeConstruction.h:226-237 (`xenodon convert`).
+ * heuristic 0 = --chan-diff (param 0..255), 1 = --std-dev; type 0 sparse, 1 dag, 2 rope.
+ * *nodes_out is allocated by the library; release with xn_free. */
+typedef struct xn_build_stats {
+    uint64_t total_leaves, unique_leaves, total_nodes, depth;
+} xn_build_stats;
+XN_API int xn_build_octree(const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz, int heuristic,
+                           double param, int type, xn_node** nodes_out, uint64_t* count_out,
+                           uint64_t* side_out, xn_build_stats* stats_out);
+XN_API void xn_free(void* p);
+
+/* HeadlessConfig, src/backend/headless/HeadlessConfig.cpp:5-28 (`device { vkindex offset extent }`) */
+typedef struct xn_headless_device {
+    uint32_t vkindex;
+    xn_rect region;
+} xn_headless_device;
+XN_API int xn_headless_config_parse(const char* text, xn_headless_device* out, int cap, int* count_out);
+
+/* ScriptCameraController, src/camera/ScriptCameraController.cpp:4-41: 9 floats per frame
+ * (forward, up, translation).  frames_out receives up to cap*9 floats. */
+XN_API int xn_camera_script_parse(const char* text, float* frames_out, int cap_frames, int* count_out);
+
+/* RenderStatsAccumulator::save, src/render/RenderStats.cpp:127-159 */
+XN_API int xn_stats_write(const char* path, const xn_render_stats* frames, uint64_t n_frames,
+                          double wall_seconds);
+
+/* PNG writer for HeadlessDisplay::save (RGBA8, src/backend/headless/HeadlessDisplay.cpp:78-91) */
+XN_API int xn_png_write(const char* path, const uint32_t* rgba, uint32_t w, uint32_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XENODON_B200_H */

@@ -1,0 +1,730 @@
+// xn_capi.cu -- implementation of the C ABI declared in include/xenodon_b200.h.
+// One xn_ctx = one CUDA device + one stream + one offscreen RGBA8 target + one resident
+// volume (grid and/or octree).  No CPU fallback: every compute entry point fails with
+// XN_ERR_CUDA when the CUDA runtime cannot provide a device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "host/xn_host.hpp"
+#include "xenodon_b200.h"
+#include "xn_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+    g_last_error = msg;
+    return status;
+}
+
+struct CudaError {
+    cudaError_t e;
+    const char* what;
+};
+#define XN_CUDA(call)                                \
+    do {                                             \
+        cudaError_t e__ = (call);                    \
+        if (e__ != cudaSuccess) throw CudaError{e__, #call}; \
+    } while (0)
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return XN_OK;
+    } catch (const xn::Error& e) {
+        return fail(e.status, e.what());
+    } catch (const CudaError& e) {
+        cudaGetLastError(); // clear sticky-less errors
+        return fail(XN_ERR_CUDA, std::string(e.what) + ": " + cudaGetErrorString(e.e));
+    } catch (const std::bad_alloc&) {
+        return fail(XN_ERR_LIMIT, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(XN_ERR_INVALID, e.what());
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) XN_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+const char* const TRAVERSAL_NAMES[5] = {"dda", "svo-naive", "esvo", "svo-df", "svo-rope"};
+
+} // namespace
+
+struct xn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timing_pending = false;
+    double last_ms = 0;
+
+    // volume
+    uint32_t* grid = nullptr;
+    uint64_t nx = 0, ny = 0, nz = 0;
+    xn::DNode* nodes = nullptr;
+    uint64_t node_count = 0, side = 0;
+    uint32_t root_meta = 0, max_depth = 0;
+
+    // target
+    xn_rect output{0, 0, 0, 0}, display{0, 0, 0, 0};
+    bool have_target = false;
+    uint32_t* own_target = nullptr;
+    uint64_t own_target_px = 0;
+    uint32_t* ext_target = nullptr;
+    uint64_t ext_stride = 0;
+
+    // params
+    float ratio[3] = {1, 1, 1};
+    uint32_t model_dim[3] = {0, 0, 0};
+    float emission = 1.0f;
+    bool have_params = false;
+
+    std::vector<void*> ipc_opened;
+
+    void free_grid() {
+        if (grid) cudaFree(grid);
+        grid = nullptr;
+        nx = ny = nz = 0;
+    }
+    void free_nodes() {
+        if (nodes) cudaFree(nodes);
+        nodes = nullptr;
+        node_count = side = 0;
+    }
+};
+
+namespace {
+
+void check_ctx(const xn_ctx* ctx) {
+    if (!ctx) throw xn::Error(XN_ERR_INVALID, "null context");
+}
+
+void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[3], const float tr[3],
+                 xn::FrameParams& p) {
+    if (traversal < 0 || traversal > 4) throw xn::Error(XN_ERR_INVALID, "Invalid shader");
+    if (!ctx->have_target) throw xn::Error(XN_ERR_INVALID, "xn_set_target has not been called");
+    if (!ctx->have_params) throw xn::Error(XN_ERR_INVALID, "xn_set_params has not been called");
+    if (!fwd || !up || !tr) throw xn::Error(XN_ERR_INVALID, "null camera vector");
+    if (traversal == XN_DDA) {
+        if (!ctx->grid)
+            throw xn::Error(XN_ERR_INVALID, "Shader 'dda' is incompatible with model type 'svo' (requires 'tiff')");
+    } else if (!ctx->nodes) {
+        throw xn::Error(XN_ERR_INVALID, std::string("Shader '") + TRAVERSAL_NAMES[traversal] +
+                                            "' is incompatible with model type 'tiff' (requires 'svo')");
+    }
+    std::memset(&p, 0, sizeof p);
+    for (int i = 0; i < 3; ++i) {
+        p.fwd[i] = fwd[i];
+        p.up[i] = up[i];
+        p.pos[i] = tr[i] / ctx->ratio[i]; // pre-divide, src/render/Renderer.cpp:62 (binary32)
+        p.ratio[i] = ctx->ratio[i];
+        p.model_dim[i] = ctx->model_dim[i];
+    }
+    p.out_x = ctx->output.x;
+    p.out_y = ctx->output.y;
+    p.out_w = ctx->output.w;
+    p.out_h = ctx->output.h;
+    p.disp_x = ctx->display.x;
+    p.disp_y = ctx->display.y;
+    p.disp_w = ctx->display.w;
+    p.disp_h = ctx->display.h;
+    p.emission = ctx->emission;
+    if (ctx->ext_target) {
+        p.target = ctx->ext_target;
+        p.target_stride = ctx->ext_stride;
+    } else {
+        p.target = ctx->own_target;
+        p.target_stride = ctx->output.w;
+    }
+    p.grid = ctx->grid;
+    p.nx = (uint32_t)ctx->nx;
+    p.ny = (uint32_t)ctx->ny;
+    p.nz = (uint32_t)ctx->nz;
+    p.nodes = ctx->nodes;
+    p.root_meta = ctx->root_meta;
+    p.max_depth = ctx->max_depth;
+}
+
+void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) {
+    // d_raw: count 40-byte nodes on the device; produce the 64-byte resident layout
+    ctx->free_nodes();
+    XN_CUDA(cudaMalloc(&ctx->nodes, count * sizeof(xn::DNode)));
+    uint32_t* d_max = nullptr;
+    XN_CUDA(cudaMalloc(&d_max, sizeof(uint32_t)));
+    XN_CUDA(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), ctx->stream));
+    XN_CUDA(xn::launch_relayout(d_raw, count, ctx->nodes, d_max, ctx->stream));
+    uint32_t root[2] = {0, 0};
+    XN_CUDA(cudaMemcpyAsync(root, (const uint8_t*)d_raw + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t maxd = 0;
+    XN_CUDA(cudaMemcpyAsync(&maxd, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    XN_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_max);
+    if (maxd > 23) {
+        ctx->free_nodes();
+        throw xn::Error(XN_ERR_LIMIT, "octree deeper than 23 levels (the traversal stack depth of the reference)");
+    }
+    ctx->root_meta = xn::make_meta(root[0], root[1]);
+    ctx->max_depth = maxd;
+    ctx->node_count = count;
+    ctx->side = side;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* xn_last_error(void) { return g_last_error.c_str(); }
+const char* xn_version(void) { return "xenodon-b200 0.1 (sm_100a)"; }
+
+int xn_traversal_from_name(const char* name) {
+    if (!name) return XN_ERR_INVALID;
+    for (int i = 0; i < 5; ++i)
+        if (std::strcmp(name, TRAVERSAL_NAMES[i]) == 0) return i;
+    return fail(XN_ERR_INVALID, std::string("Invalid shader '") + name + "'");
+}
+const char* xn_traversal_name(int t) { return t >= 0 && t < 5 ? TRAVERSAL_NAMES[t] : "?"; }
+
+int xn_device_count(int* count) {
+    return guarded([&] {
+        if (!count) throw xn::Error(XN_ERR_INVALID, "null argument");
+        *count = 0;
+        XN_CUDA(cudaGetDeviceCount(count));
+    });
+}
+
+int xn_device_name(int device, char* buf, size_t cap) {
+    return guarded([&] {
+        if (!buf || cap == 0) throw xn::Error(XN_ERR_INVALID, "null argument");
+        cudaDeviceProp prop;
+        XN_CUDA(cudaGetDeviceProperties(&prop, device));
+        std::snprintf(buf, cap, "%s", prop.name);
+    });
+}
+
+int xn_ctx_create(int cuda_device, xn_ctx** out) {
+    return guarded([&] {
+        if (!out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        *out = nullptr;
+        int n = 0;
+        XN_CUDA(cudaGetDeviceCount(&n));
+        if (cuda_device < 0 || cuda_device >= n)
+            throw xn::Error(XN_ERR_INVALID, "device index " + std::to_string(cuda_device) + " out of range (" +
+                                                std::to_string(n) + " CUDA devices)");
+        DeviceGuard g(cuda_device);
+        auto ctx = std::make_unique<xn_ctx>();
+        ctx->device = cuda_device;
+        XN_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        XN_CUDA(cudaEventCreate(&ctx->ev_start));
+        XN_CUDA(cudaEventCreate(&ctx->ev_stop));
+        XN_CUDA(xn::configure_kernels());
+        *out = ctx.release();
+    });
+}
+
+int xn_ctx_destroy(xn_ctx* ctx) {
+    return guarded([&] {
+        if (!ctx) return;
+        DeviceGuard g(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
+        ctx->free_grid();
+        ctx->free_nodes();
+        if (ctx->own_target) cudaFree(ctx->own_target);
+        cudaEventDestroy(ctx->ev_start);
+        cudaEventDestroy(ctx->ev_stop);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    });
+}
+
+int xn_ctx_device(const xn_ctx* ctx) { return ctx ? ctx->device : XN_ERR_INVALID; }
+
+// ---- volumes ----
+
+static void check_grid_dims(uint64_t nx, uint64_t ny, uint64_t nz) {
+    if (nx == 0 || ny == 0 || nz == 0) throw xn::Error(XN_ERR_INVALID, "empty grid");
+    if (nx > 0xFFFFFFFFull || ny > 0xFFFFFFFFull || nz > 0xFFFFFFFFull)
+        throw xn::Error(XN_ERR_LIMIT, "grid dimension exceeds 2^32 - 1");
+}
+
+int xn_upload_grid(xn_ctx* ctx, const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!rgba) throw xn::Error(XN_ERR_INVALID, "null grid");
+        check_grid_dims(nx, ny, nz);
+        DeviceGuard g(ctx->device);
+        ctx->free_grid();
+        const uint64_t bytes = nx * ny * nz * 4;
+        XN_CUDA(cudaMalloc(&ctx->grid, bytes));
+        // bulk copy in 256 MiB pieces (pageable source; replaces the reference's scalar
+        // element-wise staging loop, src/render/DdaRaytraceAlgorithm.cpp:61-63)
+        const uint64_t piece = 256ull << 20;
+        for (uint64_t off = 0; off < bytes; off += piece)
+            XN_CUDA(cudaMemcpyAsync((uint8_t*)ctx->grid + off, rgba + off, std::min(piece, bytes - off),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->nx = nx;
+        ctx->ny = ny;
+        ctx->nz = nz;
+    });
+}
+
+int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t ny, uint64_t nz) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!d_rgba) throw xn::Error(XN_ERR_INVALID, "null grid");
+        check_grid_dims(nx, ny, nz);
+        DeviceGuard g(ctx->device);
+        ctx->free_grid();
+        const uint64_t bytes = nx * ny * nz * 4;
+        XN_CUDA(cudaMalloc(&ctx->grid, bytes));
+        XN_CUDA(cudaMemcpyAsync(ctx->grid, d_rgba, bytes, cudaMemcpyDefault, ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->nx = nx;
+        ctx->ny = ny;
+        ctx->nz = nz;
+    });
+}
+
+int xn_upload_svo(xn_ctx* ctx, const xn_node* nodes, uint64_t count, uint64_t side) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!nodes || count == 0) throw xn::Error(XN_ERR_INVALID, "empty octree");
+        if (count > 0xFFFFFFFFull) throw xn::Error(XN_ERR_LIMIT, "octree exceeds 2^32 - 1 nodes");
+        DeviceGuard g(ctx->device);
+        void* d_raw = nullptr;
+        XN_CUDA(cudaMalloc(&d_raw, count * sizeof(xn_node)));
+        try {
+            const uint64_t bytes = count * sizeof(xn_node), piece = 256ull << 20;
+            for (uint64_t off = 0; off < bytes; off += piece)
+                XN_CUDA(cudaMemcpyAsync((uint8_t*)d_raw + off, (const uint8_t*)nodes + off,
+                                        std::min(piece, bytes - off), cudaMemcpyHostToDevice, ctx->stream));
+            finish_svo_upload(ctx, d_raw, count, side);
+        } catch (...) {
+            cudaFree(d_raw);
+            throw;
+        }
+        cudaFree(d_raw);
+    });
+}
+
+int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uint64_t side) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!d_nodes40 || count == 0) throw xn::Error(XN_ERR_INVALID, "empty octree");
+        if (count > 0xFFFFFFFFull) throw xn::Error(XN_ERR_LIMIT, "octree exceeds 2^32 - 1 nodes");
+        DeviceGuard g(ctx->device);
+        finish_svo_upload(ctx, const_cast<void*>(d_nodes40), count, side);
+    });
+}
+
+int xn_synth_grid_device(xn_ctx* ctx, int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t seed) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (kind < 0 || kind > 1) throw xn::Error(XN_ERR_INVALID, "unknown synthetic volume kind");
+        check_grid_dims(nx, ny, nz);
+        if (nx > 0xFFFFu || ny > 0xFFFFu || nz > 0xFFFFu) throw xn::Error(XN_ERR_LIMIT, "synthetic grid too large");
+        DeviceGuard g(ctx->device);
+        ctx->free_grid();
+        XN_CUDA(cudaMalloc(&ctx->grid, nx * ny * nz * 4));
+        const xn::SynthSpec spec{(uint32_t)kind, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz, seed};
+        XN_CUDA(xn::launch_synth(ctx->grid, spec, ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->nx = nx;
+        ctx->ny = ny;
+        ctx->nz = nz;
+    });
+}
+
+int xn_synth_grid_host(int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t seed, uint8_t* rgba_out) {
+    return guarded([&] {
+        if (!rgba_out) throw xn::Error(XN_ERR_INVALID, "null output");
+        xn::synth_grid_host(kind, nx, ny, nz, seed, rgba_out);
+    });
+}
+
+int xn_download_grid(xn_ctx* ctx, uint8_t* rgba_out, uint64_t cap_bytes) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!ctx->grid) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
+        const uint64_t bytes = ctx->nx * ctx->ny * ctx->nz * 4;
+        if (!rgba_out || cap_bytes < bytes) throw xn::Error(XN_ERR_INVALID, "output buffer too small");
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaMemcpyAsync(rgba_out, ctx->grid, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---- target / params ----
+
+int xn_set_target(xn_ctx* ctx, const xn_rect* output, const xn_rect* display) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!output || !display) throw xn::Error(XN_ERR_INVALID, "null rectangle");
+        if (display->w == 0 || display->h == 0) throw xn::Error(XN_ERR_INVALID, "empty display region");
+        DeviceGuard g(ctx->device);
+        const uint64_t px = (uint64_t)output->w * output->h;
+        if (px > ctx->own_target_px) {
+            if (ctx->own_target) cudaFree(ctx->own_target);
+            ctx->own_target = nullptr;
+            ctx->own_target_px = 0;
+            XN_CUDA(cudaMalloc(&ctx->own_target, std::max<uint64_t>(px, 1) * 4));
+            ctx->own_target_px = px;
+        }
+        ctx->output = *output;
+        ctx->display = *display;
+        ctx->have_target = true;
+    });
+}
+
+int xn_set_params(xn_ctx* ctx, const float voxel_ratio[3], const uint32_t model_dim[3], float emission_coeff) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!voxel_ratio || !model_dim) throw xn::Error(XN_ERR_INVALID, "null argument");
+        for (int i = 0; i < 3; ++i) {
+            if (!(voxel_ratio[i] > 0.0f)) throw xn::Error(XN_ERR_INVALID, "voxel ratio must be positive");
+            ctx->ratio[i] = voxel_ratio[i];
+            ctx->model_dim[i] = model_dim[i];
+        }
+        if (!(emission_coeff >= 0.0f)) throw xn::Error(XN_ERR_INVALID, "emission coefficient must be >= 0");
+        ctx->emission = emission_coeff;
+        ctx->have_params = true;
+    });
+}
+
+int xn_set_target_buffer(xn_ctx* ctx, void* device_ptr, size_t stride_px) {
+    return guarded([&] {
+        check_ctx(ctx);
+        ctx->ext_target = (uint32_t*)device_ptr;
+        ctx->ext_stride = device_ptr ? stride_px : 0;
+        if (device_ptr && stride_px < ctx->output.w && ctx->have_target)
+            throw xn::Error(XN_ERR_INVALID, "target stride smaller than the region width");
+    });
+}
+
+// ---- frames ----
+
+int xn_render(xn_ctx* ctx, int traversal, const float forward[3], const float up[3], const float translation[3]) {
+    return guarded([&] {
+        check_ctx(ctx);
+        xn::FrameParams p;
+        fill_params(ctx, traversal, forward, up, translation, p);
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->stream));
+        XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+        ctx->timing_pending = true;
+    });
+}
+
+int xn_sync(xn_ctx* ctx, double* kernel_ms) {
+    return guarded([&] {
+        check_ctx(ctx);
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->timing_pending) {
+            float ms = 0;
+            XN_CUDA(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+            ctx->last_ms = ms;
+            ctx->timing_pending = false;
+        }
+        if (kernel_ms) *kernel_ms = ctx->last_ms;
+    });
+}
+
+int xn_download(xn_ctx* ctx, uint32_t* dst, size_t stride_px) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!dst) throw xn::Error(XN_ERR_INVALID, "null destination");
+        if (!ctx->have_target) throw xn::Error(XN_ERR_INVALID, "xn_set_target has not been called");
+        const uint32_t w = ctx->output.w, h = ctx->output.h;
+        if (stride_px == 0) stride_px = w;
+        if (stride_px < w) throw xn::Error(XN_ERR_INVALID, "stride smaller than the region width");
+        if (w == 0 || h == 0) return;
+        DeviceGuard g(ctx->device);
+        const uint32_t* src = ctx->ext_target ? ctx->ext_target : ctx->own_target;
+        const size_t src_stride = ctx->ext_target ? ctx->ext_stride : w;
+        XN_CUDA(cudaMemcpy2DAsync(dst, stride_px * 4, src, src_stride * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int xn_render_stats_pass(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                         const float translation[3], uint32_t* steps_out, uint64_t* bytes_out,
+                         uint64_t totals_out[2]) {
+    return guarded([&] {
+        check_ctx(ctx);
+        xn::FrameParams p;
+        fill_params(ctx, traversal, forward, up, translation, p);
+        DeviceGuard g(ctx->device);
+        const uint64_t n = (uint64_t)p.out_w * p.out_h;
+        if (totals_out) totals_out[0] = totals_out[1] = 0;
+        if (n == 0) return;
+        uint32_t* d_steps = nullptr;
+        unsigned long long *d_bytes = nullptr, *d_tot = nullptr;
+        uint32_t* d_scratch_target = nullptr;
+        try {
+            XN_CUDA(cudaMalloc(&d_steps, n * 4));
+            XN_CUDA(cudaMalloc(&d_bytes, n * 8));
+            XN_CUDA(cudaMalloc(&d_tot, 16));
+            // the stats pass must not disturb the image of a previous xn_render
+            XN_CUDA(cudaMalloc(&d_scratch_target, n * 4));
+            XN_CUDA(cudaMemsetAsync(d_tot, 0, 16, ctx->stream));
+            p.steps_out = d_steps;
+            p.bytes_out = d_bytes;
+            p.target = d_scratch_target;
+            p.target_stride = p.out_w;
+            XN_CUDA(xn::launch_traversal(traversal, p, true, ctx->stream));
+            XN_CUDA(xn::launch_stats_totals(d_steps, d_bytes, n, d_tot, ctx->stream));
+            if (steps_out) XN_CUDA(cudaMemcpyAsync(steps_out, d_steps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (bytes_out) XN_CUDA(cudaMemcpyAsync(bytes_out, d_bytes, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            unsigned long long tot[2] = {0, 0};
+            XN_CUDA(cudaMemcpyAsync(tot, d_tot, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            XN_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (totals_out) {
+                totals_out[0] = tot[0];
+                totals_out[1] = tot[1];
+            }
+        } catch (...) {
+            cudaFree(d_steps);
+            cudaFree(d_bytes);
+            cudaFree(d_tot);
+            cudaFree(d_scratch_target);
+            throw;
+        }
+        cudaFree(d_steps);
+        cudaFree(d_bytes);
+        cudaFree(d_tot);
+        cudaFree(d_scratch_target);
+    });
+}
+
+// ---- multi-device gather ----
+
+int xn_frame_gather(xn_ctx* const* ctxs, int n, uint32_t* host_dst, xn_rect* enclosing_out) {
+    return guarded([&] {
+        if (!ctxs || n <= 0 || !host_dst) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        for (int i = 0; i < n; ++i) {
+            check_ctx(ctxs[i]);
+            if (!ctxs[i]->have_target) throw xn::Error(XN_ERR_INVALID, "context without a target");
+        }
+        xn_rect enc = ctxs[0]->output;
+        for (int i = 1; i < n; ++i) enc = xn::rect_union(enc, ctxs[i]->output);
+        if (enclosing_out) *enclosing_out = enc;
+        const uint64_t px = (uint64_t)enc.w * enc.h;
+        if (px == 0) return;
+        xn_ctx* root = ctxs[0];
+        DeviceGuard g(root->device);
+        uint32_t* frame = nullptr;
+        XN_CUDA(cudaMalloc(&frame, px * 4));
+        try {
+            // background 0xFF000000 (BLACK_PIXEL, HeadlessDisplay.cpp:11): memset 0 then alpha
+            // via a 2-D memset of the top byte is awkward; fill from the host once instead.
+            std::vector<uint32_t> bg;
+            bool covered = false;
+            for (int i = 0; i < n && !covered; ++i)
+                covered = ctxs[i]->output.w == enc.w && ctxs[i]->output.h == enc.h;
+            if (!covered) {
+                bg.assign(px, 0xFF000000u);
+                XN_CUDA(cudaMemcpyAsync(frame, bg.data(), px * 4, cudaMemcpyHostToDevice, root->stream));
+                XN_CUDA(cudaStreamSynchronize(root->stream));
+            }
+            for (int i = 0; i < n; ++i) {
+                const xn_ctx* c = ctxs[i];
+                if (c->output.w == 0 || c->output.h == 0) continue;
+                const uint32_t* src = c->ext_target ? c->ext_target : c->own_target;
+                const size_t src_stride = c->ext_target ? c->ext_stride : c->output.w;
+                uint32_t* dst = frame + (uint64_t)(c->output.y - enc.y) * enc.w + (uint64_t)(c->output.x - enc.x);
+                // UVA peer copy: goes over NVLink when peer access is possible, staged otherwise
+                XN_CUDA(cudaMemcpy2DAsync(dst, (size_t)enc.w * 4, src, src_stride * 4, (size_t)c->output.w * 4,
+                                          c->output.h, cudaMemcpyDefault, root->stream));
+            }
+            XN_CUDA(cudaMemcpyAsync(host_dst, frame, px * 4, cudaMemcpyDeviceToHost, root->stream));
+            XN_CUDA(cudaStreamSynchronize(root->stream));
+        } catch (...) {
+            cudaFree(frame);
+            throw;
+        }
+        cudaFree(frame);
+    });
+}
+
+int xn_frame_buffer_create(xn_ctx* ctx, uint32_t w, uint32_t h, void** device_ptr_out, uint8_t handle_out[64]) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!device_ptr_out || w == 0 || h == 0) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        DeviceGuard g(ctx->device);
+        void* p = nullptr;
+        const uint64_t px = (uint64_t)w * h;
+        XN_CUDA(cudaMalloc(&p, px * 4));
+        std::vector<uint32_t> bg(px, 0xFF000000u);
+        XN_CUDA(cudaMemcpy(p, bg.data(), px * 4, cudaMemcpyHostToDevice));
+        if (handle_out) {
+            cudaIpcMemHandle_t hnd;
+            cudaError_t e = cudaIpcGetMemHandle(&hnd, p);
+            if (e != cudaSuccess) {
+                cudaFree(p);
+                throw CudaError{e, "cudaIpcGetMemHandle"};
+            }
+            std::memcpy(handle_out, &hnd, 64);
+        }
+        *device_ptr_out = p;
+    });
+}
+
+int xn_frame_buffer_open(xn_ctx* ctx, const uint8_t handle[64], void** device_ptr_out) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!handle || !device_ptr_out) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        DeviceGuard g(ctx->device);
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, handle, 64);
+        void* p = nullptr;
+        XN_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened.push_back(p);
+        *device_ptr_out = p;
+    });
+}
+
+int xn_frame_buffer_close(xn_ctx* ctx, void* device_ptr) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!device_ptr) return;
+        DeviceGuard g(ctx->device);
+        auto it = std::find(ctx->ipc_opened.begin(), ctx->ipc_opened.end(), device_ptr);
+        if (it != ctx->ipc_opened.end()) {
+            ctx->ipc_opened.erase(it);
+            XN_CUDA(cudaIpcCloseMemHandle(device_ptr));
+        } else {
+            XN_CUDA(cudaFree(device_ptr));
+        }
+    });
+}
+
+int xn_frame_buffer_read(xn_ctx* ctx, const void* device_ptr, uint32_t w, uint32_t h, uint32_t* host_dst) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!device_ptr || !host_dst) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaMemcpyAsync(host_dst, device_ptr, (uint64_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---- host formats ----
+
+int xn_tiff_info(const char* path, uint64_t dims_out[3]) {
+    return guarded([&] {
+        if (!path || !dims_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        const auto info = xn::tiff_info(path);
+        dims_out[0] = info.nx;
+        dims_out[1] = info.ny;
+        dims_out[2] = info.nz;
+    });
+}
+int xn_tiff_read(const char* path, uint8_t* rgba_out, uint64_t cap_bytes) {
+    return guarded([&] {
+        if (!path || !rgba_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        xn::tiff_read(path, rgba_out, cap_bytes);
+    });
+}
+int xn_tiff_write(const char* path, const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz, int bigtiff) {
+    return guarded([&] {
+        if (!path || !rgba) throw xn::Error(XN_ERR_INVALID, "null argument");
+        xn::tiff_write(path, rgba, nx, ny, nz, bigtiff != 0);
+    });
+}
+int xn_svo_info(const char* path, uint64_t* side_out, uint64_t* count_out) {
+    return guarded([&] {
+        if (!path) throw xn::Error(XN_ERR_INVALID, "null argument");
+        uint64_t side, count;
+        xn::svo_info(path, side, count);
+        if (side_out) *side_out = side;
+        if (count_out) *count_out = count;
+    });
+}
+int xn_svo_read(const char* path, xn_node* nodes_out, uint64_t cap_nodes) {
+    return guarded([&] {
+        if (!path || !nodes_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        xn::svo_read(path, nodes_out, cap_nodes);
+    });
+}
+int xn_svo_write(const char* path, const xn_node* nodes, uint64_t count, uint64_t side) {
+    return guarded([&] {
+        if (!path || !nodes) throw xn::Error(XN_ERR_INVALID, "null argument");
+        xn::save_svo(path, nodes, count, side);
+    });
+}
+
+int xn_build_octree(const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz, int heuristic, double param, int type,
+                    xn_node** nodes_out, uint64_t* count_out, uint64_t* side_out, xn_build_stats* stats_out) {
+    return guarded([&] {
+        if (!rgba || !nodes_out || !count_out || !side_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        if (heuristic < 0 || heuristic > 1 || type < 0 || type > 2) throw xn::Error(XN_ERR_INVALID, "bad option");
+        xn::Octree t = xn::build_octree(rgba, nx, ny, nz, (xn::Heuristic)heuristic, param, (xn::OctreeType)type, stats_out);
+        xn_node* out = (xn_node*)std::malloc(std::max<size_t>(t.nodes.size(), 1) * sizeof(xn_node));
+        if (!out) throw std::bad_alloc();
+        std::memcpy(out, t.nodes.data(), t.nodes.size() * sizeof(xn_node));
+        *nodes_out = out;
+        *count_out = t.nodes.size();
+        *side_out = t.side;
+    });
+}
+
+void xn_free(void* p) { std::free(p); }
+
+int xn_headless_config_parse(const char* text, xn_headless_device* out, int cap, int* count_out) {
+    return guarded([&] {
+        if (!text || !count_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        const auto devs = xn::parse_headless_config(text);
+        *count_out = (int)devs.size();
+        if (out)
+            for (int i = 0; i < cap && i < (int)devs.size(); ++i) out[i] = devs[i];
+    });
+}
+
+int xn_camera_script_parse(const char* text, float* frames_out, int cap_frames, int* count_out) {
+    return guarded([&] {
+        if (!text || !count_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        const auto frames = xn::parse_camera_script(text);
+        *count_out = (int)frames.size();
+        if (frames_out)
+            for (int i = 0; i < cap_frames && i < (int)frames.size(); ++i) {
+                std::memcpy(frames_out + 9 * i, frames[i].forward, 12);
+                std::memcpy(frames_out + 9 * i + 3, frames[i].up, 12);
+                std::memcpy(frames_out + 9 * i + 6, frames[i].translation, 12);
+            }
+    });
+}
+
+int xn_stats_write(const char* path, const xn_render_stats* frames, uint64_t n_frames, double wall_seconds) {
+    return guarded([&] {
+        if (!path || (!frames && n_frames)) throw xn::Error(XN_ERR_INVALID, "null argument");
+        xn::stats_write(path, frames, n_frames, wall_seconds);
+    });
+}
+
+int xn_png_write(const char* path, const uint32_t* rgba, uint32_t w, uint32_t h) {
+    return guarded([&] {
+        if (!path || !rgba) throw xn::Error(XN_ERR_INVALID, "null argument");
+        xn::png_write(path, rgba, w, h);
+    });
+}
+
+} // extern "C"

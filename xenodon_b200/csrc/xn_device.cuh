@@ -1,0 +1,149 @@
+// xn_device.cuh -- device-side types and binary32 helpers shared by the traversal kernels.
+//
+// Arithmetic contract: every geometric quantity (ray set-up, slab tests, DDA side
+// distances, octree descent decisions) is computed in IEEE binary32 in the order the
+// reference shader source writes it, with no FMA contraction (this translation unit is
+// compiled with -fmad=false and uses IEEE division / square root), so the sequence of
+// voxels / nodes a ray visits is identical to the CPU oracle's.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace xn {
+
+// ---------------------------------------------------------------------------------
+// Device volume layouts
+// ---------------------------------------------------------------------------------
+
+// Octree node as resident in HBM: 8 child descriptors of 8 bytes, 64-byte aligned, so one
+// 64-bit load yields everything the shaders read about a child with three dependent 32-bit
+// loads (children[i], nodes[child].is_leaf_depth, nodes[child].color; resources/octree.glsl:6-14).
+//   slot.x = child node index (for a rope-file leaf, slots 0..5 are the ropes)
+//   slot.y = meta of THAT child: bit 31 leaf | depth << 24 | b << 16 | g << 8 | r
+struct __align__(64) DNode {
+    uint2 slot[8];
+};
+static_assert(sizeof(DNode) == 64, "device node must be 64 bytes");
+
+constexpr uint32_t META_LEAF = 0x80000000u;
+__host__ __device__ inline uint32_t make_meta(uint32_t color, uint32_t is_leaf_depth) {
+    return (is_leaf_depth & META_LEAF) | ((is_leaf_depth & 0x1Fu) << 24) | (color & 0x00FFFFFFu);
+}
+__device__ __forceinline__ bool meta_is_leaf(uint32_t m) { return (m & META_LEAF) != 0u; }
+__device__ __forceinline__ uint32_t meta_depth(uint32_t m) { return (m >> 24) & 0x1Fu; }
+
+// ---------------------------------------------------------------------------------
+// Per-frame kernel parameters (push constants + uniform buffer of the reference,
+// resources/common.glsl:6-35), passed by value as a __grid_constant__.
+// ---------------------------------------------------------------------------------
+struct FrameParams {
+    float fwd[3], up[3], pos[3]; // pos = translation / voxel_ratio (src/render/Renderer.cpp:62)
+    int32_t out_x, out_y;
+    uint32_t out_w, out_h;
+    int32_t disp_x, disp_y;
+    uint32_t disp_w, disp_h;
+    float ratio[3];
+    uint32_t model_dim[3];
+    float emission;
+
+    uint32_t* target;      // RGBA8 pixels, may point into a peer device's frame
+    uint64_t target_stride; // in pixels
+
+    const uint32_t* grid;   // RGBA8 voxels, x fastest
+    uint32_t nx, ny, nz;
+    const DNode* nodes;
+    uint32_t root_meta;
+    uint32_t max_depth;     // deepest node depth in the tree (stack sizing)
+
+    uint32_t* steps_out;            // stats pass only
+    unsigned long long* bytes_out;  // stats pass only
+};
+
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 F3(float x, float y, float z) { return f3{x, y, z}; }
+
+// GLSL min/max: min(x, y) = y < x ? y : x.  Identical to fminf/fmaxf for the finite,
+// non-signed-zero-sensitive values on this path; the select form is used where a zero of
+// either sign can appear so results stay bit-identical to the oracle.
+__device__ __forceinline__ float gmin(float a, float b) { return b < a ? b : a; }
+__device__ __forceinline__ float gmax(float a, float b) { return a < b ? b : a; }
+__device__ __forceinline__ float min_elem(f3 v) { return gmin(v.x, gmin(v.y, v.z)); }
+__device__ __forceinline__ float max_elem(f3 v) { return gmax(v.x, gmax(v.y, v.z)); }
+__device__ __forceinline__ float gsign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+__device__ __forceinline__ float gmod(float x, float y) { return x - y * floorf(x / y); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return F3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ __forceinline__ f3 normalize3(f3 a) {
+    float len = sqrtf(dot3(a, a));
+    return F3(a.x / len, a.y / len, a.z / len);
+}
+
+// exact (float)b / 255.0f for b in 0..255 without an IEEE division: one multiply by the
+// rounded reciprocal plus one FMA Newton correction (verified for all 256 inputs in
+// tests/test_host_logic.py::test_unorm8_reciprocal_identity).
+__device__ __forceinline__ float unorm8(uint32_t b) {
+    const float r = 1.0f / 255.0f;
+    float x = (float)b;
+    float q = x * r;
+    float rem = __fmaf_rn(-q, 255.0f, x);
+    return __fmaf_rn(rem, r, q);
+}
+
+// imageStore to rgba8: clamp to [0,1], scale by 255, round half to even; NaN -> 0
+__device__ __forceinline__ uint32_t pack_unorm8(float v) {
+    if (!(v > 0.0f)) return 0u;
+    if (v > 1.0f) v = 1.0f;
+    return (uint32_t)__float2uint_rn(v * 255.0f);
+}
+
+// resources/common.glsl:40-56 -- camera ray for a pixel, in the reference's operation order
+__device__ __forceinline__ f3 make_ray(const FrameParams& p, int32_t pixel_x, int32_t pixel_y) {
+    float uvx = (float)(pixel_x - p.disp_x) / (float)p.disp_w;
+    float uvy = (float)(pixel_y - p.disp_y) / (float)p.disp_h;
+    uvx -= 0.5f;
+    uvy -= 0.5f;
+    uvy *= (float)p.disp_h / (float)p.disp_w;
+
+    f3 dir = F3(p.fwd[0], p.fwd[1], p.fwd[2]);
+    f3 up = F3(p.up[0], p.up[1], p.up[2]);
+    f3 right = normalize3(cross3(up, dir));
+    up = normalize3(cross3(right, dir));
+
+    f3 rd = F3((uvx * right.x + uvy * up.x) + dir.x, (uvx * right.y + uvy * up.y) + dir.y,
+               (uvx * right.z + uvy * up.z) + dir.z);
+    rd = normalize3(rd);
+    rd = normalize3(F3(rd.x / p.ratio[0], rd.y / p.ratio[1], rd.z / p.ratio[2]));
+
+    const float epsilon = 1.1920928955078125e-07f; // exp2(-23)
+    if (fabsf(rd.x) < epsilon) rd.x = epsilon;
+    if (fabsf(rd.y) < epsilon) rd.y = epsilon;
+    if (fabsf(rd.z) < epsilon) rd.z = epsilon;
+    return rd;
+}
+
+// resources/common.glsl:68-72
+__device__ __forceinline__ float voxel_emission_coeff(const FrameParams& p, f3 rd) {
+    f3 rd2 = F3(rd.x * rd.x, rd.y * rd.y, rd.z * rd.z);
+    f3 dim2 = F3(p.ratio[0] * p.ratio[0], p.ratio[1] * p.ratio[1], p.ratio[2] * p.ratio[2]);
+    return p.emission * sqrtf(dot3(rd2, dim2) / dot3(rd2, F3(1.f, 1.f, 1.f)));
+}
+
+__device__ __forceinline__ uint32_t pack_pixel(f3 c) {
+    return pack_unorm8(c.x) | (pack_unorm8(c.y) << 8) | (pack_unorm8(c.z) << 16) | 0xFF000000u;
+}
+
+// Pixel owned by this thread: each warp shades an 8x4 pixel tile (rays of a warp stay
+// spatially coherent), a 256-thread block covers 16x16 pixels.
+constexpr int BLOCK_THREADS = 256;
+constexpr int BLOCK_W = 16, BLOCK_H = 16;
+__device__ __forceinline__ void thread_pixel(uint32_t& ix, uint32_t& iy) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    ix = blockIdx.x * BLOCK_W + (warp & 1u) * 8u + (lane & 7u);
+    iy = blockIdx.y * BLOCK_H + (warp >> 1) * 4u + (lane >> 3);
+}
+
+} // namespace xn

@@ -117,6 +117,14 @@ XN_API int xn_set_target(xn_ctx* ctx, const xn_rect* output, const xn_rect* disp
  * model_dim = grid dimensions for tiff volumes, side^3 for svo volumes. */
 XN_API int xn_set_params(xn_ctx* ctx, const float voxel_ratio[3], const uint32_t model_dim[3],
                          float emission_coeff);
+/* Row interleave: render only the 16-row stripes s of the output region with
+ * s % count == index.  This is the partition `count` sets of 16-row `device {}` blocks would
+ * express in a headless configuration, done in one launch per device so that GPUs sharing a
+ * frame get balanced work (edge bands of a frame mostly miss the volume).  Pixels of stripes
+ * the context does not own are left untouched.  Default (1, 0) = the whole region.
+ * xn_owned_rays returns the number of pixels the context shades per frame. */
+XN_API int xn_set_interleave(xn_ctx* ctx, uint32_t count, uint32_t index);
+XN_API int xn_owned_rays(const xn_ctx* ctx, uint64_t* rays);
 /* Redirect the render target: pixels of this context's region are stored at
  * device_ptr[y * stride_px + x] (x, y relative to the region).  device_ptr may be
  * memory of a PEER device (NVLink): the traversal kernel then stores finished pixels
@@ -138,6 +146,25 @@ XN_API int xn_sync(xn_ctx* ctx, double* kernel_ms);
 /* HeadlessOutput::download, src/backend/headless/HeadlessOutput.cpp:95-136:
  * copies the region's pixels to dst[y * stride_px + x]; stride_px 0 = region width. */
 XN_API int xn_download(xn_ctx* ctx, uint32_t* dst, size_t stride_px);
+
+/* Pipelined frame output (replaces the blocking staging copy of HeadlessOutput::download,
+ * src/backend/headless/HeadlessOutput.cpp:95-136, for movie rendering): renders into one of
+ * two alternating device targets and copies the finished region to host_dst (tight rows,
+ * region w*h pixels; pinned memory from xn_host_alloc makes the copy asynchronous) on a
+ * second stream, so the copy of frame i overlaps the traversal of frame i+1.  host_dst is
+ * valid after the next xn_sync.  Not combinable with xn_set_target_buffer. */
+XN_API int xn_render_download_async(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                                    const float translation[3], uint32_t* host_dst);
+XN_API int xn_host_alloc(size_t bytes, void** out); /* page-locked host memory */
+XN_API int xn_host_free(void* p);
+
+/* Device-side stopwatch over any span of calls on this context: xn_mark(ctx, 0) and
+ * xn_mark(ctx, 1) record events on the context's stream; xn_mark_elapsed waits for the
+ * stream and returns the device time between them (ms). */
+XN_API int xn_mark(xn_ctx* ctx, int which);
+XN_API int xn_mark_elapsed(xn_ctx* ctx, double* ms);
+/* number of traversal-kernel launches this context has enqueued so far */
+XN_API int xn_launch_count(const xn_ctx* ctx, uint64_t* count);
 
 /* Instrumented frame (not timed): per-ray trace() loop iterations and algorithmic
  * bytes (4 B per texel fetch / node-field read as the shader source writes them).

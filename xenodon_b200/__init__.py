@@ -83,11 +83,20 @@ _PROTOTYPES = {
     "xn_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "xn_set_target": (C.c_int, [C.c_void_p, C.POINTER(Rect), C.POINTER(Rect)]),
     "xn_set_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_uint32 * 3), C.c_float]),
+    "xn_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "xn_owned_rays": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "xn_set_target_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "xn_render": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
                             C.POINTER(C.c_float * 3)]),
     "xn_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "xn_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "xn_render_download_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
+                                           C.POINTER(C.c_float * 3), C.c_void_p]),
+    "xn_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "xn_host_free": (C.c_int, [C.c_void_p]),
+    "xn_mark": (C.c_int, [C.c_void_p, C.c_int]),
+    "xn_mark_elapsed": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "xn_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "xn_render_stats_pass": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
                                        C.POINTER(C.c_float * 3), C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_uint64 * 2)]),
@@ -319,6 +328,14 @@ class Context:
         r = _f3(voxel_ratio)
         _check(lib().xn_set_params(self._h, C.byref(r), C.byref(md), float(emission)))
 
+    def set_interleave(self, count: int, index: int):
+        _check(lib().xn_set_interleave(self._h, count, index))
+
+    def owned_rays(self) -> int:
+        n = C.c_uint64()
+        _check(lib().xn_owned_rays(self._h, C.byref(n)))
+        return n.value
+
     def set_target_buffer(self, device_ptr, stride_px: int):
         _check(lib().xn_set_target_buffer(self._h, device_ptr, stride_px))
 
@@ -326,6 +343,25 @@ class Context:
         t = TRAVERSALS[traversal] if isinstance(traversal, str) else traversal
         f, u, p = _f3(camera[0]), _f3(camera[1]), _f3(camera[2])
         _check(lib().xn_render(self._h, t, C.byref(f), C.byref(u), C.byref(p)))
+
+    def render_download_async(self, traversal, camera, host_frame: "PinnedFrame"):
+        """Pipelined frame: traversal + asynchronous copy-out into pinned host memory."""
+        t = TRAVERSALS[traversal] if isinstance(traversal, str) else traversal
+        f, u, p = _f3(camera[0]), _f3(camera[1]), _f3(camera[2])
+        _check(lib().xn_render_download_async(self._h, t, C.byref(f), C.byref(u), C.byref(p), host_frame.ptr))
+
+    def mark(self, which: int):
+        _check(lib().xn_mark(self._h, which))
+
+    def mark_elapsed(self) -> float:
+        ms = C.c_double()
+        _check(lib().xn_mark_elapsed(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _check(lib().xn_launch_count(self._h, C.byref(n)))
+        return n.value
 
     def sync(self) -> float:
         ms = C.c_double()
@@ -372,6 +408,22 @@ class Context:
         out = np.empty((h, w, 4), dtype=np.uint8)
         _check(lib().xn_frame_buffer_read(self._h, ptr, w, h, out.ctypes.data))
         return out
+
+
+class PinnedFrame:
+    """Page-locked host frame (h, w, 4) uint8 for asynchronous copy-out."""
+
+    def __init__(self, w: int, h: int):
+        p = C.c_void_p()
+        _check(lib().xn_host_alloc(w * h * 4, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.frombuffer((C.c_uint8 * (w * h * 4)).from_address(self.ptr), dtype=np.uint8).reshape(h, w, 4)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().xn_host_free(self.ptr)
+            self.ptr = None
 
 
 @dataclass

@@ -69,7 +69,17 @@ struct xn_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     bool timing_pending = false;
+    uint64_t launches = 0;
+
+    // pipelined frame output: two alternating targets + a copy stream
+    cudaStream_t copy_stream = nullptr;
+    uint32_t* pipe_target[2] = {nullptr, nullptr};
+    uint64_t pipe_target_px = 0;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool copy_in_flight[2] = {false, false};
+    int pipe_next = 0;
     double last_ms = 0;
 
     // volume
@@ -92,6 +102,8 @@ struct xn_ctx {
     uint32_t model_dim[3] = {0, 0, 0};
     float emission = 1.0f;
     bool have_params = false;
+
+    uint32_t il_count = 1, il_index = 0;
 
     std::vector<void*> ipc_opened;
 
@@ -157,6 +169,8 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.nodes = ctx->nodes;
     p.root_meta = ctx->root_meta;
     p.max_depth = ctx->max_depth;
+    p.il_count = ctx->il_count;
+    p.il_index = ctx->il_index;
 }
 
 void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) {
@@ -230,6 +244,13 @@ int xn_ctx_create(int cuda_device, xn_ctx** out) {
         XN_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         XN_CUDA(cudaEventCreate(&ctx->ev_start));
         XN_CUDA(cudaEventCreate(&ctx->ev_stop));
+        XN_CUDA(cudaEventCreate(&ctx->ev_mark[0]));
+        XN_CUDA(cudaEventCreate(&ctx->ev_mark[1]));
+        XN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
+            XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        }
         XN_CUDA(xn::configure_kernels());
         *out = ctx.release();
     });
@@ -240,6 +261,14 @@ int xn_ctx_destroy(xn_ctx* ctx) {
         if (!ctx) return;
         DeviceGuard g(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
+            if (ctx->ev_mark[i]) cudaEventDestroy(ctx->ev_mark[i]);
+            if (ctx->ev_rendered[i]) cudaEventDestroy(ctx->ev_rendered[i]);
+            if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        }
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
         ctx->free_grid();
         ctx->free_nodes();
@@ -406,6 +435,25 @@ int xn_set_params(xn_ctx* ctx, const float voxel_ratio[3], const uint32_t model_
     });
 }
 
+int xn_set_interleave(xn_ctx* ctx, uint32_t count, uint32_t index) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (count == 0 || index >= count) throw xn::Error(XN_ERR_INVALID, "interleave index must be < count");
+        ctx->il_count = count;
+        ctx->il_index = index;
+    });
+}
+
+int xn_owned_rays(const xn_ctx* ctx, uint64_t* rays) {
+    if (!ctx || !rays) return fail(XN_ERR_INVALID, "null argument");
+    uint64_t rows = 0;
+    const uint32_t bh = xn::BLOCK_H;
+    for (uint32_t s = ctx->il_index, y = s * bh; y < ctx->output.h; s += ctx->il_count, y = s * bh)
+        rows += std::min<uint64_t>(bh, ctx->output.h - y);
+    *rays = rows * ctx->output.w;
+    return XN_OK;
+}
+
 int xn_set_target_buffer(xn_ctx* ctx, void* device_ptr, size_t stride_px) {
     return guarded([&] {
         check_ctx(ctx);
@@ -428,7 +476,92 @@ int xn_render(xn_ctx* ctx, int traversal, const float forward[3], const float up
         XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->stream));
         XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
         ctx->timing_pending = true;
+        ++ctx->launches;
     });
+}
+
+int xn_render_download_async(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                             const float translation[3], uint32_t* host_dst) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!host_dst) throw xn::Error(XN_ERR_INVALID, "null destination");
+        if (ctx->ext_target) throw xn::Error(XN_ERR_INVALID, "pipelined output cannot target an external buffer");
+        xn::FrameParams p;
+        fill_params(ctx, traversal, forward, up, translation, p);
+        DeviceGuard g(ctx->device);
+        const uint64_t px = (uint64_t)p.out_w * p.out_h;
+        if (px == 0) return;
+        if (px > ctx->pipe_target_px) {
+            XN_CUDA(cudaStreamSynchronize(ctx->stream));
+            XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            for (int i = 0; i < 2; ++i) {
+                if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
+                ctx->pipe_target[i] = nullptr;
+                ctx->copy_in_flight[i] = false;
+            }
+            ctx->pipe_target_px = 0;
+            XN_CUDA(cudaMalloc(&ctx->pipe_target[0], px * 4));
+            XN_CUDA(cudaMalloc(&ctx->pipe_target[1], px * 4));
+            ctx->pipe_target_px = px;
+        }
+        const int b = ctx->pipe_next;
+        ctx->pipe_next ^= 1;
+        // the traversal may only overwrite target b once its previous copy-out has finished
+        if (ctx->copy_in_flight[b]) XN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        p.target = ctx->pipe_target[b];
+        p.target_stride = p.out_w;
+        XN_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->stream));
+        XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+        XN_CUDA(cudaEventRecord(ctx->ev_rendered[b], ctx->stream));
+        XN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[b], 0));
+        XN_CUDA(cudaMemcpyAsync(host_dst, ctx->pipe_target[b], px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        XN_CUDA(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        ctx->copy_in_flight[b] = true;
+        ctx->timing_pending = true;
+        ++ctx->launches;
+    });
+}
+
+int xn_host_alloc(size_t bytes, void** out) {
+    return guarded([&] {
+        if (!out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        *out = nullptr;
+        XN_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    });
+}
+
+int xn_host_free(void* p) {
+    return guarded([&] {
+        if (p) XN_CUDA(cudaFreeHost(p));
+    });
+}
+
+int xn_mark(xn_ctx* ctx, int which) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (which < 0 || which > 1) throw xn::Error(XN_ERR_INVALID, "mark index must be 0 or 1");
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaEventRecord(ctx->ev_mark[which], ctx->stream));
+    });
+}
+
+int xn_mark_elapsed(xn_ctx* ctx, double* ms) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!ms) throw xn::Error(XN_ERR_INVALID, "null argument");
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaEventSynchronize(ctx->ev_mark[1]));
+        float f = 0;
+        XN_CUDA(cudaEventElapsedTime(&f, ctx->ev_mark[0], ctx->ev_mark[1]));
+        *ms = f;
+    });
+}
+
+int xn_launch_count(const xn_ctx* ctx, uint64_t* count) {
+    if (!ctx || !count) return fail(XN_ERR_INVALID, "null argument");
+    *count = ctx->launches;
+    return XN_OK;
 }
 
 int xn_sync(xn_ctx* ctx, double* kernel_ms) {
@@ -436,6 +569,10 @@ int xn_sync(xn_ctx* ctx, double* kernel_ms) {
         check_ctx(ctx);
         DeviceGuard g(ctx->device);
         XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->copy_in_flight[0] || ctx->copy_in_flight[1]) {
+            XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            ctx->copy_in_flight[0] = ctx->copy_in_flight[1] = false;
+        }
         if (ctx->timing_pending) {
             float ms = 0;
             XN_CUDA(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
@@ -485,6 +622,9 @@ int xn_render_stats_pass(xn_ctx* ctx, int traversal, const float forward[3], con
             // the stats pass must not disturb the image of a previous xn_render
             XN_CUDA(cudaMalloc(&d_scratch_target, n * 4));
             XN_CUDA(cudaMemsetAsync(d_tot, 0, 16, ctx->stream));
+            // rows of stripes this context does not own (xn_set_interleave) report zero
+            XN_CUDA(cudaMemsetAsync(d_steps, 0, n * 4, ctx->stream));
+            XN_CUDA(cudaMemsetAsync(d_bytes, 0, n * 8, ctx->stream));
             p.steps_out = d_steps;
             p.bytes_out = d_bytes;
             p.target = d_scratch_target;

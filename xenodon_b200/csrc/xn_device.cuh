@@ -55,6 +55,10 @@ struct FrameParams {
     uint32_t root_meta;
     uint32_t max_depth;     // deepest node depth in the tree (stack sizing)
 
+    // row interleave: this launch shades only the 16-row stripes s with s % il_count == il_index
+    // (the same partition as il_count*... `device {}` blocks of 16 rows each, in one launch)
+    uint32_t il_count, il_index;
+
     uint32_t* steps_out;            // stats pass only
     unsigned long long* bytes_out;  // stats pass only
 };
@@ -140,10 +144,10 @@ __device__ __forceinline__ uint32_t pack_pixel(f3 c) {
 // spatially coherent), a 256-thread block covers 16x16 pixels.
 constexpr int BLOCK_THREADS = 256;
 constexpr int BLOCK_W = 16, BLOCK_H = 16;
-__device__ __forceinline__ void thread_pixel(uint32_t& ix, uint32_t& iy) {
+__device__ __forceinline__ void thread_pixel(const FrameParams& p, uint32_t& ix, uint32_t& iy) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     ix = blockIdx.x * BLOCK_W + (warp & 1u) * 8u + (lane & 7u);
-    iy = blockIdx.y * BLOCK_H + (warp >> 1) * 4u + (lane >> 3);
+    iy = (blockIdx.y * p.il_count + p.il_index) * BLOCK_H + (warp >> 1) * 4u + (lane >> 3);
 }
 
 } // namespace xn

@@ -44,7 +44,7 @@ __device__ __forceinline__ void store_result(const FrameParams& p, uint32_t ix, 
 template <bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
-    thread_pixel(ix, iy);
+    thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
     RayStats<STATS> st;
 
@@ -167,7 +167,7 @@ __device__ __forceinline__ void node_slab(f3 offset, float side, f3 rrd, f3 bias
 template <bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) svo_naive_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
-    thread_pixel(ix, iy);
+    thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
     RayStats<STATS> st;
     const float MIN_STEP_SIZE = 0.00001f;
@@ -216,7 +216,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) svo_df_kernel(const __grid_constant__ FrameParams p) {
     extern __shared__ uint2 df_stack[]; // [level][thread]
     uint32_t ix, iy;
-    thread_pixel(ix, iy);
+    thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
     RayStats<STATS> st;
 
@@ -297,7 +297,7 @@ template <bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_constant__ FrameParams p) {
     extern __shared__ uint2 esvo_stack[]; // [level][thread] = (parent, bits(t_max))
     uint32_t ix, iy;
-    thread_pixel(ix, iy);
+    thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
     RayStats<STATS> st;
     const uint32_t cast_stack_depth = 23u;
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
 template <bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) svo_rope_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
-    thread_pixel(ix, iy);
+    thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
     RayStats<STATS> st;
 
@@ -500,7 +500,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_rope_kernel(const __grid_co
 // ---------------------------------------------------------------------------------
 template <bool STATS>
 static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t stream) {
-    const dim3 grid((p.out_w + BLOCK_W - 1) / BLOCK_W, (p.out_h + BLOCK_H - 1) / BLOCK_H, 1);
+    const uint32_t stripes = (p.out_h + BLOCK_H - 1) / BLOCK_H;
+    if (p.il_count == 0 || p.il_index >= p.il_count) return cudaErrorInvalidValue;
+    const uint32_t owned = stripes > p.il_index ? (stripes - p.il_index + p.il_count - 1) / p.il_count : 0;
+    if (owned == 0) return cudaSuccess;
+    const dim3 grid((p.out_w + BLOCK_W - 1) / BLOCK_W, owned, 1);
     const dim3 block(BLOCK_THREADS, 1, 1);
     const size_t stack_bytes = (size_t)(p.max_depth + 1u) * BLOCK_THREADS * sizeof(uint2);
     switch (traversal) {

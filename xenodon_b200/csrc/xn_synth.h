@@ -124,9 +124,14 @@ XN_HD uint32_t synth_tng(const SynthSpec& s, uint32_t x, uint32_t y, uint32_t z)
     const uint32_t r1 = synth_ridged(s, x, y, z, s0, s.seed);
     const uint32_t r2 = synth_ridged(s, x, y, z, s0, s.seed + 101u);
     const uint32_t r = r1 < r2 ? r1 : r2;
-    const uint32_t lo = 44000u; // ~8-10 % of voxels end above the colour map's floor
+    // tools/make-tng-volume.py normalises log-density between a low percentile (90th for the
+    // 1024^3 volume, 96th for 2048^3) and the 99th percentile and clips; the constants below are
+    // those percentiles of this ridge field (measured once; the field's distribution does not
+    // depend on the volume size), so ~90 % / ~96 % of voxels sit at the colour map's floor.
+    const uint32_t lo = maxdim >= 2048u ? 58410u : 54150u;
+    const uint32_t hi = 61960u;
     if (r <= lo) return synth_magma(0);
-    const uint32_t t = ((r - lo) * 255u) / (65535u - lo);
+    const uint32_t t = ((r - lo) * 255u) / (hi - lo);
     return synth_magma(t > 255u ? 255u : t);
 }
 

@@ -6,8 +6,10 @@ CAM_ORBIT = ((0.125333, 0, 0.992115), (0, 1, 0), (0.249334, 0.5, -1.48423))  # c
 CAM_INSIDE = ((-0.0627904, 2.75301e-07, 0.998027), (-1.21213e-09, -1, 2.75769e-07),
               (0.531395, 0.5, 0.000985205))  # camera.txt line 100: origin inside the volume
 CAM_OBLIQUE = ((0.3, -0.5, 0.7), (0.1, 1, 0.2), (0.2, 1.4, -0.3))
+# looks at the centre of a volume stretched by --voxel-ratio 1:2:0.5 from outside, obliquely
+CAM_ANISO = ((0.47, -0.6, 0.62), (0.1, 1, 0.2), (-0.6, 2.4, -1.2))
 CAM_AXIS_NEG = ((0, 0, -1), (0, 1, 0), (0.5, 0.5, 2.5))
-CAMERAS = {"single": CAM_SINGLE, "orbit": CAM_ORBIT, "inside": CAM_INSIDE, "oblique": CAM_OBLIQUE,
+CAMERAS = {"single": CAM_SINGLE, "orbit": CAM_ORBIT, "inside": CAM_INSIDE, "oblique": CAM_OBLIQUE, "aniso": CAM_ANISO,
            "axis_neg": CAM_AXIS_NEG}
 
 

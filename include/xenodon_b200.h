@@ -117,6 +117,16 @@ XN_API int xn_set_target(xn_ctx* ctx, const xn_rect* output, const xn_rect* disp
  * model_dim = grid dimensions for tiff volumes, side^3 for svo volumes. */
 XN_API int xn_set_params(xn_ctx* ctx, const float voxel_ratio[3], const uint32_t model_dim[3],
                          float emission_coeff);
+/* Arithmetic mode of the traversal kernels.  In both modes the ray geometry (which voxels /
+ * nodes a ray visits and every segment length) is computed in binary32 in the operation order
+ * of the reference shaders, so per-ray step counts equal the CPU restatement exactly.
+ *   XN_PRECISION_STRICT: colour accumulation also follows the shader's order: images are
+ *                        bit-identical to the CPU restatement of the shaders (validation mode);
+ *   XN_PRECISION_FAST  : (default) the colour sum is accumulated with fused multiply-adds on the
+ *                        raw 8-bit colours and scaled once per ray; within 1/255 per channel of
+ *                        STRICT on every pixel (identical on the vast majority). */
+enum { XN_PRECISION_FAST = 0, XN_PRECISION_STRICT = 1 };
+XN_API int xn_set_precision(xn_ctx* ctx, int mode);
 /* Row interleave: render only the 16-row stripes s of the output region with
  * s % count == index.  This is the partition `count` sets of 16-row `device {}` blocks would
  * express in a headless configuration, done in one launch per device so that GPUs sharing a

@@ -15,8 +15,19 @@ SVO_TRAVERSALS = ["svo-naive", "svo-df", "esvo", "svo-rope"]
 
 
 def _compare(xb, xo, traversal, *, grid=None, tree=None, camera, output, display, ratio=(1, 1, 1), emission=1.0):
+    """Runs both arithmetic modes.  STRICT must be bit-identical to the oracle; FAST (the default
+    mode) must visit exactly the same voxels / nodes and stay within 1/255 on every pixel."""
+    img = _compare_mode(xb, xo, traversal, True, grid=grid, tree=tree, camera=camera, output=output,
+                        display=display, ratio=ratio, emission=emission)
+    _compare_mode(xb, xo, traversal, False, grid=grid, tree=tree, camera=camera, output=output, display=display,
+                  ratio=ratio, emission=emission)
+    return img
+
+
+def _compare_mode(xb, xo, traversal, strict, *, grid, tree, camera, output, display, ratio, emission):
     ctx = xb.Context(0)
     try:
+        ctx.set_precision(strict)
         if traversal == "dda":
             ctx.upload_grid(xb.Grid(grid))
         else:
@@ -39,7 +50,12 @@ def _compare(xb, xo, traversal, *, grid=None, tree=None, camera, output, display
     assert np.array_equal(steps, rsteps), f"{traversal}: per-ray step counts differ from the oracle"
     assert np.array_equal(nbytes, rbytes), f"{traversal}: per-ray algorithmic bytes differ from the oracle"
     assert totals == (int(rsteps.sum()), int(rbytes.sum()))
-    assert np.array_equal(img, ref), f"{traversal}: image differs (max diff {mx}, {frac:.4%} of pixels > 1/255)"
+    if strict:
+        assert np.array_equal(img, ref), f"{traversal}: image differs (max diff {mx}, {frac:.4%} of pixels > 1/255)"
+    else:
+        assert mx <= 1, f"{traversal} (fast mode): max diff {mx}, {frac:.4%} of pixels > 1/255"
+        differing = float((img != ref).any(axis=-1).mean())
+        assert differing <= 0.02, f"{traversal} (fast mode): {differing:.3%} of pixels differ by 1/255"
     assert np.array_equal(img, img_after), "the stats pass must not disturb the rendered image"
     assert ms > 0
     return img

@@ -83,6 +83,7 @@ _PROTOTYPES = {
     "xn_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "xn_set_target": (C.c_int, [C.c_void_p, C.POINTER(Rect), C.POINTER(Rect)]),
     "xn_set_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_uint32 * 3), C.c_float]),
+    "xn_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "xn_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "xn_owned_rays": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "xn_set_target_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -327,6 +328,10 @@ class Context:
         md = (C.c_uint32 * 3)(*(model_dim or self.model_dim))
         r = _f3(voxel_ratio)
         _check(lib().xn_set_params(self._h, C.byref(r), C.byref(md), float(emission)))
+
+    def set_precision(self, strict: bool):
+        """strict=True: bit-identical to the CPU restatement of the shaders; False (default): fast mode."""
+        _check(lib().xn_set_precision(self._h, 1 if strict else 0))
 
     def set_interleave(self, count: int, index: int):
         _check(lib().xn_set_interleave(self._h, count, index))

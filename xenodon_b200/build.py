@@ -25,7 +25,8 @@ NVCC_KERNEL_FLAGS = ["-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-Xcompile
 NVCC_HOST_FLAGS = ["-O2", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-pthread"]
 
-CU_SOURCES = [("xn_kernels.cu", NVCC_KERNEL_FLAGS), ("xn_capi.cu", NVCC_HOST_FLAGS)]
+CU_SOURCES = [("xn_kernels.cu", NVCC_KERNEL_FLAGS), ("xn_util_kernels.cu", NVCC_HOST_FLAGS),
+              ("xn_capi.cu", NVCC_HOST_FLAGS)]
 CPP_SOURCES = ["host/xn_tiff.cpp", "host/xn_svo.cpp", "host/xn_text.cpp", "host/xn_png.cpp", "host/xn_synth_host.cpp"]
 CLI_SOURCES = ["host/xn_cli.cpp"]
 

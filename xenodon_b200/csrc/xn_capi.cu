@@ -104,6 +104,7 @@ struct xn_ctx {
     bool have_params = false;
 
     uint32_t il_count = 1, il_index = 0;
+    bool strict = false;
 
     std::vector<void*> ipc_opened;
 
@@ -435,6 +436,15 @@ int xn_set_params(xn_ctx* ctx, const float voxel_ratio[3], const uint32_t model_
     });
 }
 
+int xn_set_precision(xn_ctx* ctx, int mode) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (mode != XN_PRECISION_FAST && mode != XN_PRECISION_STRICT)
+            throw xn::Error(XN_ERR_INVALID, "unknown precision mode");
+        ctx->strict = mode == XN_PRECISION_STRICT;
+    });
+}
+
 int xn_set_interleave(xn_ctx* ctx, uint32_t count, uint32_t index) {
     return guarded([&] {
         check_ctx(ctx);
@@ -473,7 +483,7 @@ int xn_render(xn_ctx* ctx, int traversal, const float forward[3], const float up
         fill_params(ctx, traversal, forward, up, translation, p);
         DeviceGuard g(ctx->device);
         XN_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
-        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->stream));
+        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->strict, ctx->stream));
         XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
         ctx->timing_pending = true;
         ++ctx->launches;
@@ -511,7 +521,7 @@ int xn_render_download_async(xn_ctx* ctx, int traversal, const float forward[3],
         p.target = ctx->pipe_target[b];
         p.target_stride = p.out_w;
         XN_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
-        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->stream));
+        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->strict, ctx->stream));
         XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
         XN_CUDA(cudaEventRecord(ctx->ev_rendered[b], ctx->stream));
         XN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[b], 0));
@@ -629,7 +639,7 @@ int xn_render_stats_pass(xn_ctx* ctx, int traversal, const float forward[3], con
             p.bytes_out = d_bytes;
             p.target = d_scratch_target;
             p.target_stride = p.out_w;
-            XN_CUDA(xn::launch_traversal(traversal, p, true, ctx->stream));
+            XN_CUDA(xn::launch_traversal(traversal, p, true, ctx->strict, ctx->stream));
             XN_CUDA(xn::launch_stats_totals(d_steps, d_bytes, n, d_tot, ctx->stream));
             if (steps_out) XN_CUDA(cudaMemcpyAsync(steps_out, d_steps, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
             if (bytes_out) XN_CUDA(cudaMemcpyAsync(bytes_out, d_bytes, n * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,87 @@
+// xn_util_kernels.cu -- volume re-layout, synthetic-volume and statistics kernels (sm_100a).
+#include "xn_device.cuh"
+#include "xn_kernels.h"
+#include "xn_synth.h"
+
+namespace xn {
+
+// ---------------------------------------------------------------------------------
+// volume re-layout: 40-byte file nodes -> 64-byte device nodes (one thread per node)
+// ---------------------------------------------------------------------------------
+__global__ void relayout_nodes_kernel(const uint32_t* __restrict__ raw, uint64_t count, DNode* __restrict__ out,
+                                      uint32_t* __restrict__ max_depth) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t my_depth = 0;
+    if (i < count) {
+        const uint32_t* n = raw + i * 10u;
+        my_depth = n[9] & 0x7FFFFFFFu;
+        DNode d;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t child = n[c];
+            if (child >= count) child = 0; // malformed file: never index out of bounds
+            const uint32_t* cn = raw + (uint64_t)child * 10u;
+            d.slot[c] = make_uint2(child, make_meta(cn[8], cn[9]));
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + i);
+        o[0] = make_uint4(d.slot[0].x, d.slot[0].y, d.slot[1].x, d.slot[1].y);
+        o[1] = make_uint4(d.slot[2].x, d.slot[2].y, d.slot[3].x, d.slot[3].y);
+        o[2] = make_uint4(d.slot[4].x, d.slot[4].y, d.slot[5].x, d.slot[5].y);
+        o[3] = make_uint4(d.slot[6].x, d.slot[6].y, d.slot[7].x, d.slot[7].y);
+    }
+    // block-wide max of depth -> one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) my_depth = max(my_depth, __shfl_xor_sync(0xFFFFFFFFu, my_depth, o));
+    if ((threadIdx.x & 31) == 0 && my_depth) atomicMax(max_depth, my_depth);
+}
+
+cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth,
+                            cudaStream_t stream) {
+    const int threads = 256;
+    const uint64_t blocks = (count + threads - 1) / threads;
+    relayout_nodes_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, out, d_max_depth);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// synthetic volumes (bit-identical to the host generator in xn_synth.h)
+// ---------------------------------------------------------------------------------
+__global__ void synth_kernel(uint32_t* __restrict__ grid, SynthSpec spec) {
+    const uint64_t n = (uint64_t)spec.nx * spec.ny * spec.nz;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = (uint32_t)(i % spec.nx);
+        const uint32_t y = (uint32_t)((i / spec.nx) % spec.ny);
+        const uint32_t z = (uint32_t)(i / ((uint64_t)spec.nx * spec.ny));
+        grid[i] = synth_voxel(spec, x, y, z);
+    }
+}
+
+cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t stream) {
+    synth_kernel<<<148 * 16, 256, 0, stream>>>(grid, spec);
+    return cudaGetLastError();
+}
+
+// sum reduction of the stats arrays (totals for the roofline accounting)
+__global__ void stats_totals_kernel(const uint32_t* __restrict__ steps, const unsigned long long* __restrict__ bytes,
+                                    uint64_t n, unsigned long long* __restrict__ totals) {
+    unsigned long long s = 0, b = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        s += steps[i];
+        b += bytes[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&totals[0], s);
+        atomicAdd(&totals[1], b);
+    }
+}
+
+cudaError_t launch_stats_totals(const uint32_t* steps, const unsigned long long* bytes, uint64_t n,
+                                unsigned long long* totals, cudaStream_t stream) {
+    stats_totals_kernel<<<148 * 4, 256, 0, stream>>>(steps, bytes, n, totals);
+    return cudaGetLastError();
+}
+
+} // namespace xn

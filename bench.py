@@ -56,13 +56,8 @@ def log(*a):
 
 
 def frame_for(base, n_gpus, weak):
-    """Frame size with ~n_gpus times the rays of `base` at the same aspect ratio."""
-    w, h = base
-    if not weak or n_gpus == 1:
-        return w, h
-    hh = int(round(h * math.sqrt(n_gpus) / 16.0)) * 16
-    ww = int(round(hh * w / h))
-    return ww, hh
+    from xenodon_b200 import distributed as xd
+    return xd.frame_for(base, n_gpus, weak)
 
 
 class ClockSampler:
@@ -263,8 +258,8 @@ def main():
             frame_ptr = ctx.frame_buffer_open(obj[0])
         ctx.set_target_buffer(frame_ptr, W)
     else:
-        rows = [(H * r) // n_gpus for r in range(n_gpus + 1)]
-        rows = [(y // 16) * 16 for y in rows[:-1]] + [H]
+        from xenodon_b200 import distributed as xd
+        rows = xd.band_rows(H, n_gpus)
         band = (0, rows[rank], W, rows[rank + 1] - rows[rank])
         ctx.set_target(band, display)
     my_rays = ctx.owned_rays()

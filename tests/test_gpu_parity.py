@@ -4,12 +4,16 @@ exactly -- per-ray step counts and algorithmic byte counts are compared bit for 
 RGBA8 image must be identical (the kernels keep the shaders' binary32 operation order).
 The bar BASELINE.json states is <= 1/255 per channel on >= 99.9 % of pixels; these tests
 hold the stricter bit-exact bar and would report the looser one on failure."""
+import os
+
 import numpy as np
 import pytest
 
 from util import CAMERAS, blobby_grid, image_diff, random_grid
 
 pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SVO_TRAVERSALS = ["svo-naive", "svo-df", "esvo", "svo-rope"]
 
@@ -185,3 +189,30 @@ def test_device_synthetic_volumes_match_host_generator(xb):
         host = xb.Grid.synthetic(kind, *dims, seed=1729).data
         assert np.array_equal(dev, host)
         assert (dev[..., 3] == 255).all() and dev[..., :3].any()
+
+
+def test_dda_64bit_index_kernel_matches_oracle(xb):
+    """Grids of 2^31 voxels and more (2048^3) run the 64-bit-index instantiation; XN_FORCE_IDX64=1
+    runs that same kernel on a small grid so it can be compared with the oracle (subprocess: the
+    knob is read once per process)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import xenodon_b200 as xb; from oracle import xo; from util import CAMERAS, random_grid\n"
+        "g = random_grid(np.random.default_rng(64), 48, 31, 40)\n"
+        "for cam in ('orbit', 'inside', 'axis_neg'):\n"
+        "    for strict in (True, False):\n"
+        "        ctx = xb.Context(0); ctx.set_precision(strict); ctx.upload_grid(xb.Grid(g))\n"
+        "        ctx.set_target((0, 0, 160, 90)); ctx.set_params((1, 1, 1), None, 2.0)\n"
+        "        ctx.render('dda', CAMERAS[cam]); ctx.sync(); img = ctx.download()\n"
+        "        steps = ctx.stats_pass('dda', CAMERAS[cam])[0]; ctx.close()\n"
+        "        ref, rsteps, _ = xo.render('dda', grid=g, camera=CAMERAS[cam], output=(0, 0, 160, 90), emission=2.0)\n"
+        "        assert np.array_equal(steps, rsteps)\n"
+        "        d = np.abs(img.astype(int) - ref.astype(int)).max()\n"
+        "        assert d == 0 if strict else d <= 1, (cam, strict, d)\n"
+        "print('IDX64 OK')\n"
+    ) % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, XN_FORCE_IDX64="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "IDX64 OK" in r.stdout, r.stderr[-2000:]

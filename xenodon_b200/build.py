@@ -74,10 +74,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     nvcc, gxx = _nvcc(), _gxx()
     inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    # tuning experiments: XN_NVCC_DEFS="-DXN_FAST_I2F=0" python -m xenodon_b200.build --force
+    extra = os.environ.get("XN_NVCC_DEFS", "").split()
     objs = []
     for src, flags in CU_SOURCES:
         obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
-        cmd = [nvcc, "-ccbin", gxx, *ARCH, *flags, *inc, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, "-ccbin", gxx, *ARCH, *flags, *extra, *inc, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         _run(cmd)

@@ -17,8 +17,20 @@
 //            computed in the shader's exact order, so per-ray step counts are identical; only
 //            the colour sum is accumulated as fma(byte, length, sum) and scaled by 1/255 once
 //            per ray.  Differs from STRICT by at most 1/255 on a small fraction of pixels.
+#include <cstdlib>
+
 #include "xn_device.cuh"
 #include "xn_kernels.h"
+
+// tuning switches (A/B-tested on the B200, see profiles/): how many of the three colour
+// channels of the fast mode convert byte -> float with I2F.U8 rather than PRMT + FADD
+#ifndef XN_FAST_I2F
+#define XN_FAST_I2F 3
+#endif
+// DDA: march long in-grid stretches as unchecked segments (no per-step bounds test / position)
+#ifndef XN_DDA_SEGMENTS
+#define XN_DDA_SEGMENTS 1
+#endif
 
 namespace xn {
 
@@ -60,9 +72,11 @@ struct Accum {
             g += unorm8_exact(byte_f<1>(rgb)) * len;
             b += unorm8_exact(byte_f<2>(rgb)) * len;
         } else {
-            r = __fmaf_rn(byte_f<0>(rgb), len, r);
-            g = __fmaf_rn(byte_f<1>(rgb), len, g);
-            b = __fmaf_rn(byte_f<2>(rgb), len, b);
+            // XN_FAST_I2F of the three channels convert with I2F.U8 (one instruction on the
+            // quarter-rate conversion pipe), the rest with PRMT + FADD (ALU + FMA pipes)
+            r = __fmaf_rn(XN_FAST_I2F >= 1 ? (float)(rgb & 0xFFu) : byte_f<0>(rgb), len, r);
+            g = __fmaf_rn(XN_FAST_I2F >= 2 ? (float)((rgb >> 8) & 0xFFu) : byte_f<1>(rgb), len, g);
+            b = __fmaf_rn(XN_FAST_I2F >= 3 ? (float)((rgb >> 16) & 0xFFu) : byte_f<2>(rgb), len, b);
         }
     }
     __device__ __forceinline__ f3 finish(float ec) const {
@@ -80,6 +94,30 @@ __device__ __forceinline__ void store_result(const FrameParams& p, uint32_t ix, 
         if (p.steps_out) p.steps_out[i] = st.steps;
         if (p.bytes_out) p.bytes_out[i] = st.bytes;
     }
+}
+
+// voxel coordinates of an in-range linear index (x + y*stride_y + z*stride_z)
+__device__ __forceinline__ void recover_position(int32_t idx, int32_t stride_y, int32_t stride_z, int& px, int& py,
+                                                 int& pz) {
+    const uint32_t qz = (uint32_t)idx / (uint32_t)stride_z;
+    const uint32_t rem = (uint32_t)idx - qz * (uint32_t)stride_z;
+    const uint32_t qy = rem / (uint32_t)stride_y;
+    pz = (int)qz;
+    py = (int)qy;
+    px = (int)(rem - qy * (uint32_t)stride_y);
+}
+__device__ __forceinline__ void recover_position(int64_t idx, int64_t stride_y, int64_t stride_z, int& px, int& py,
+                                                 int& pz) {
+    // idx < 2^48: the binary64 quotient estimate is off by at most one, fixed below; the slice
+    // remainder is below 2^32 (dimensions are < 2^16), so the rest is 32-bit arithmetic
+    int64_t qz = (int64_t)((double)idx / (double)stride_z);
+    int64_t rem = idx - qz * stride_z;
+    if (rem < 0) { --qz; rem += stride_z; }
+    else if (rem >= stride_z) { ++qz; rem -= stride_z; }
+    const uint32_t qy = (uint32_t)rem / (uint32_t)stride_y;
+    pz = (int)qz;
+    py = (int)qy;
+    px = (int)((uint32_t)rem - qy * (uint32_t)stride_y);
 }
 
 // ---------------------------------------------------------------------------------
@@ -128,25 +166,118 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
         const uint32_t* __restrict__ grid = p.grid;
 
         // texelFetch; outside the grid -> 0 (border)
+        bool inr = (uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz;
         uint32_t v = 0;
-        if ((uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz) v = __ldg(grid + idx);
+        if (inr) v = __ldg(grid + idx);
 
         float t = 0.0f;
         const float t_end = t_max - t_min;
         while (t < t_end) {
-            // side distances stay finite and positive: fminf == GLSL min here
-            const bool mx = sdx <= fminf(sdy, sdz);
-            const bool my = sdy <= fminf(sdz, sdx);
-            const bool mz = sdz <= fminf(sdx, sdy);
+#if XN_DDA_SEGMENTS
+            // Unchecked segment.  From an in-range voxel with r_i steps left to the grid face on
+            // axis i, no axis can leave the grid within min(r_i) iterations (an iteration takes at
+            // most one step per axis).  Axis i takes its j-th step in the iteration that ends at
+            // side distance sd_i + (j-1)*td_i, so bounding t by min_i(sd_i + (r_i-2)*td_i) (one
+            // step of slack against rounding of the repeated additions) keeps every fetch of the
+            // segment inside the grid without tracking the position or testing bounds per step.
+            // The arithmetic on t / side distances is exactly the loop body of dda.comp:41-50.
+            if (inr) {
+                const int rx = sx > 0 ? (int)p.nx - 1 - px : px;
+                const int ry = sy > 0 ? (int)p.ny - 1 - py : py;
+                const int rz = sz > 0 ? (int)p.nz - 1 - pz : pz;
+                if (min(rx, min(ry, rz)) >= 4) {
+                    const float t_lim = fminf(
+                        t_end, fminf(sdx + (float)(rx - 2) * tdx,
+                                     fminf(sdy + (float)(ry - 2) * tdy, sdz + (float)(rz - 2) * tdz)));
+                    if (t < t_lim) {
+                        // One step advances t by at most td_min (the axis with the smallest
+                        // spacing crosses a face within td_min), so while t < t_lim - 4 td_min four
+                        // more steps are certain to be taken: they run as one TRIP without any
+                        // per-step loop test.  A trip advances the geometry of its four steps first
+                        // (it never depends on loaded data), requests their four texels together,
+                        // and only then accumulates the four texels requested by the PREVIOUS trip,
+                        // so a load has a whole trip to arrive (two register sets, a / b).
+                        const float t_lim4 = t_lim - 4.5f * fminf(tdx, fminf(tdy, tdz));
+#define XN_DDA_STEP(DT)                                            \
+    {                                                              \
+        const float t0 = fminf(sdx, fminf(sdy, sdz));              \
+        const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0; \
+        DT = t0 - t;                                               \
+        t = t0;                                                    \
+        if (mx) { sdx += tdx; idx += dix; }                        \
+        if (my) { sdy += tdy; idx += diy; }                        \
+        if (mz) { sdz += tdz; idx += diz; }                        \
+        st.step();                                                 \
+        st.read(4);                                                \
+    }
+#define XN_DDA_TRIP(N, P)                                                        \
+    {                                                                            \
+        float d0;                                                                \
+        XN_DDA_STEP(d0) N##0 = __ldg(grid + idx);                                \
+        XN_DDA_STEP(N##d1) N##1 = __ldg(grid + idx);                             \
+        XN_DDA_STEP(N##d2) N##2 = __ldg(grid + idx);                             \
+        XN_DDA_STEP(N##d3) N##3 = __ldg(grid + idx);                             \
+        acc.add(P##0, P##d1);                                                    \
+        acc.add(P##1, P##d2);                                                    \
+        acc.add(P##2, P##d3);                                                    \
+        acc.add(P##3, d0);                                                       \
+    }
+                        if (t < t_lim4) {
+                            // set a starts as "nothing pending" except the current voxel's texel
+                            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = v, b0, b1, b2, b3;
+                            float ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, bd1, bd2, bd3;
+                            for (;;) {
+                                XN_DDA_TRIP(b, a)
+                                if (!(t < t_lim4)) {
+                                    acc.add(b0, bd1);
+                                    acc.add(b1, bd2);
+                                    acc.add(b2, bd3);
+                                    v = b3;
+                                    break;
+                                }
+                                XN_DDA_TRIP(a, b)
+                                if (!(t < t_lim4)) {
+                                    acc.add(a0, ad1);
+                                    acc.add(a1, ad2);
+                                    acc.add(a2, ad3);
+                                    v = a3;
+                                    break;
+                                }
+                            }
+                        }
+#undef XN_DDA_TRIP
+                        // the last few steps of the segment, one at a time
+                        while (t < t_lim) {
+                            float dt;
+                            XN_DDA_STEP(dt)
+                            const uint32_t vn = __ldg(grid + idx);
+                            acc.add(v, dt);
+                            v = vn;
+                        }
+#undef XN_DDA_STEP
+                        // recover the voxel coordinates from the linear index (still in range)
+                        recover_position(idx, stride_y, stride_z, px, py, pz);
+                        continue;
+                    }
+                }
+            }
+#endif
+            // checked single step (grid faces, entry ties, the possible extra last iteration)
+            // side distances stay finite and non-negative, so fminf == GLSL min, and
+            // `sd.x <= min(sd.y, sd.z)` (dda.comp:42) <=> `sd.x == min(sd.x, sd.y, sd.z)`
             const float t0 = fminf(sdx, fminf(sdy, sdz));
+            const bool mx = sdx == t0;
+            const bool my = sdy == t0;
+            const bool mz = sdz == t0;
             const float dt = t0 - t;
             t = t0;
             if (mx) { sdx += tdx; px += sx; idx += dix; }
             if (my) { sdy += tdy; py += sy; idx += diy; }
             if (mz) { sdz += tdz; pz += sz; idx += diz; }
 
+            inr = (uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz;
             uint32_t vn = 0; // texel of the next step (used only if the loop continues)
-            if ((uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz) vn = __ldg(grid + idx);
+            if (inr) vn = __ldg(grid + idx);
 
             acc.add(v, dt);
             v = vn;
@@ -380,6 +511,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
     uint2* stack = stack_mem + threadIdx.x;
     const DNode* __restrict__ nodes = p.nodes;
 
+    // The child descriptor of (parent, idx) is requested at the END of the previous iteration
+    // (99.6 % of iterations consume it, ncu r01), so the t_corner arithmetic of the next
+    // iteration overlaps the load instead of waiting behind it.
+    uint2 s = load_slot(nodes, parent, idx ^ octant_mask);
+
     while (scale < cast_stack_depth) {
         st.step();
         const float tcorx = posx * tcx - tbx, tcory = posy * tcy - tby, tcorz = posz * tcz - tbz;
@@ -389,7 +525,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
             const float tv_max = fminf(t_max, tc_max);
             if (t_min <= tv_max) {
                 st.read(8); // children[idx ^ octant_mask] + nodes[child].is_leaf_depth
-                const uint2 s = load_slot(nodes, parent, idx ^ octant_mask);
                 if (meta_is_leaf(s.y)) {
                     st.read(4); // color
                     acc.add(s.y, tv_max - t_min);
@@ -411,6 +546,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
                     if (tceny > t_min) { idx ^= 2u; posy += scale_exp2; }
                     if (tcenz > t_min) { idx ^= 1u; posz += scale_exp2; }
                     t_max = tv_max;
+                    s = load_slot(nodes, parent, idx ^ octant_mask);
                     continue;
                 }
             }
@@ -431,7 +567,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
             if (ax) dbits |= __float_as_uint(posx) ^ __float_as_uint(posx + scale_exp2);
             if (ay) dbits |= __float_as_uint(posy) ^ __float_as_uint(posy + scale_exp2);
             if (az) dbits |= __float_as_uint(posz) ^ __float_as_uint(posz + scale_exp2);
-            scale = (__float_as_uint((float)dbits) >> 23) - 127u;
+            // esvo.comp:117 takes the exponent of float(dbits); dbits is a union of carry runs of
+            // at most 23 bits inside the cube (exact in binary32), so the index of its highest
+            // set bit is the same number, and anything >= 23 (or dbits == 0) leaves the loop
+            scale = 31u - (uint32_t)__clz((int)dbits);
             if (scale >= cast_stack_depth) break; // left the cube (also guards the reference's
                                                   // underflowed stack read, esvo.comp:119-123)
             scale_exp2 = __uint_as_float((scale - cast_stack_depth + 127u) << 23);
@@ -447,6 +586,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
             idx = (shx & 1u) * 4u + (shy & 1u) * 2u + (shz & 1u);
             h = 0.0f;
         }
+        s = load_slot(nodes, parent, idx ^ octant_mask);
     }
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
 }
@@ -524,6 +664,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_rope_kernel(const __grid_co
 // ---------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------
+static bool force_idx64() {
+    static const bool v = [] {
+        const char* e = getenv("XN_FORCE_IDX64");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 template <bool STATS, bool STRICT>
 static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t stream) {
     const uint32_t stripes = (p.out_h + BLOCK_H - 1) / BLOCK_H;
@@ -535,7 +683,8 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
     const bool deep = p.max_depth + 1u > 12u; // 12 stack levels cover trees up to 2048^3
     switch (traversal) {
         case 0:
-            if ((uint64_t)p.nx * p.ny * p.nz < (1ull << 31))
+            // XN_FORCE_IDX64=1 (test knob) runs the 64-bit-index kernel on small grids too
+            if ((uint64_t)p.nx * p.ny * p.nz < (1ull << 31) && !force_idx64())
                 dda_kernel<STATS, STRICT, int32_t><<<grid, block, 0, stream>>>(p);
             else
                 dda_kernel<STATS, STRICT, int64_t><<<grid, block, 0, stream>>>(p);

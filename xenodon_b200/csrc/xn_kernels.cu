@@ -27,6 +27,10 @@
 #ifndef XN_FAST_I2F
 #define XN_FAST_I2F 3
 #endif
+// octree kernels: minimum resident blocks per SM requested from the register allocator
+#ifndef XN_SVO_MIN_BLOCKS
+#define XN_SVO_MIN_BLOCKS 1
+#endif
 // DDA: march long in-grid stretches as unchecked segments (no per-step bounds test / position)
 #ifndef XN_DDA_SEGMENTS
 #define XN_DDA_SEGMENTS 1
@@ -291,6 +295,28 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------
 // shared octree helpers
 // ---------------------------------------------------------------------------------
+// Traversal stacks: [level][thread] in shared memory, addressed in the shared window directly
+// (one LEA + one LDS/STS per access; generic pointers cost five address instructions here).
+__device__ __forceinline__ uint32_t stack_base(const void* smem) {
+    uint32_t base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * (uint32_t)sizeof(uint2);
+    // opaque copy: keeps the address in a register instead of being re-derived (S2R + LEA chain)
+    // at every push and pop
+    asm volatile("mov.u32 %0, %0;" : "+r"(base));
+    return base;
+}
+__device__ __forceinline__ void stack_store(uint32_t base, uint32_t level, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(base + level * (uint32_t)(BLOCK_THREADS * sizeof(uint2))),
+                 "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ uint2 stack_load(uint32_t base, uint32_t level) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(r.x), "=r"(r.y)
+                 : "r"(base + level * (uint32_t)(BLOCK_THREADS * sizeof(uint2)))
+                 : "memory");
+    return r;
+}
 __device__ __forceinline__ uint2 load_slot(const DNode* __restrict__ nodes, uint32_t node, uint32_t child) {
     return __ldg(&nodes[node].slot[child]);
 }
@@ -345,7 +371,7 @@ __device__ __forceinline__ void node_slab(f3 offset, float side, f3 rrd, f3 bias
 // svo_naive (resources/svo_naive.comp:29-89)
 // ---------------------------------------------------------------------------------
 template <bool STATS, bool STRICT>
-__global__ void __launch_bounds__(BLOCK_THREADS) svo_naive_kernel(const __grid_constant__ FrameParams p) {
+__global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_naive_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
@@ -389,7 +415,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_naive_kernel(const __grid_c
 // the pop does not re-read is_leaf_depth (svo_df.comp:58) from memory.
 // ---------------------------------------------------------------------------------
 template <bool STATS, bool STRICT, int LEVELS>
-__global__ void __launch_bounds__(BLOCK_THREADS) svo_df_kernel(const __grid_constant__ FrameParams p) {
+__global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kernel(const __grid_constant__ FrameParams p) {
     __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS]; // [level][thread]
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
@@ -406,7 +432,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_df_kernel(const __grid_cons
     f3 pos = F3(0.f, 0.f, 0.f);
     float side = 0.5f;
     Accum<STRICT> acc;
-    uint2* stack = stack_mem + threadIdx.x;
+    const uint32_t stack = stack_base(stack_mem);
 
     for (;;) {
         st.step();
@@ -425,7 +451,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_df_kernel(const __grid_cons
                 acc.add(s.y, t_max - gmax(t_min, 0.0f));
             } else {
                 if (child_idx != 7u) {
-                    if (sp < LEVELS) stack[sp * BLOCK_THREADS] = make_uint2(node, child_idx | (depth << 3));
+                    if (sp < LEVELS) stack_store(stack, (uint32_t)sp, node, child_idx | (depth << 3));
                     ++sp;
                 }
                 side *= 0.5f;
@@ -439,7 +465,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_df_kernel(const __grid_cons
         if (child_idx == 7u) {
             --sp;
             if (sp < 0) break;
-            const uint2 e = stack[sp * BLOCK_THREADS];
+            const uint2 e = stack_load(stack, (uint32_t)sp);
             node = e.x;
             child_idx = e.y & 7u;
             depth = e.y >> 3;
@@ -465,7 +491,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) svo_df_kernel(const __grid_cons
 // LEVELS (>= tree depth) levels of shared memory are enough.
 // ---------------------------------------------------------------------------------
 template <bool STATS, bool STRICT, int LEVELS>
-__global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_constant__ FrameParams p) {
+__global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(const __grid_constant__ FrameParams p) {
     __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS]; // [level][thread] = (parent, bits(t_max))
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
@@ -508,12 +534,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
     if (1.5f * tcz - tbz > t_min) { posz = 1.5f; idx ^= 1u; }
 
     Accum<STRICT> acc;
-    uint2* stack = stack_mem + threadIdx.x;
+    const uint32_t stack = stack_base(stack_mem);
     const DNode* __restrict__ nodes = p.nodes;
 
-    // The child descriptor of (parent, idx) is requested at the END of the previous iteration
-    // (99.6 % of iterations consume it, ncu r01), so the t_corner arithmetic of the next
-    // iteration overlaps the load instead of waiting behind it.
+    // The child descriptor of (parent, idx) is requested at the END of the previous iteration,
+    // at a single load site (99.6 % of iterations consume it, ncu r01), so the t_corner
+    // arithmetic of the next iteration overlaps the load instead of waiting behind it.
     uint2 s = load_slot(nodes, parent, idx ^ octant_mask);
 
     while (scale < cast_stack_depth) {
@@ -521,6 +547,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
         const float tcorx = posx * tcx - tbx, tcory = posy * tcy - tby, tcorz = posz * tcz - tbz;
         const float tc_max = fminf(tcorx, fminf(tcory, tcorz));
 
+        bool pushed = false;
         if (t_min <= t_max) {
             const float tv_max = fminf(t_max, tc_max);
             if (t_min <= tv_max) {
@@ -532,8 +559,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
                     // PUSH
                     if (tc_max < h) {
                         const uint32_t level = (cast_stack_depth - 1u) - scale;
-                        if (level < (uint32_t)LEVELS)
-                            stack[level * BLOCK_THREADS] = make_uint2(parent, __float_as_uint(t_max));
+                        if (level < (uint32_t)LEVELS) stack_store(stack, level, parent, __float_as_uint(t_max));
                     }
                     h = tc_max;
                     parent = s.x;
@@ -546,45 +572,46 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
                     if (tceny > t_min) { idx ^= 2u; posy += scale_exp2; }
                     if (tcenz > t_min) { idx ^= 1u; posz += scale_exp2; }
                     t_max = tv_max;
-                    s = load_slot(nodes, parent, idx ^ octant_mask);
-                    continue;
+                    pushed = true;
                 }
             }
         }
 
-        // ADVANCE
-        const bool ax = tcorx <= tc_max, ay = tcory <= tc_max, az = tcorz <= tc_max;
-        const uint32_t step_mask = (ax ? 4u : 0u) | (ay ? 2u : 0u) | (az ? 1u : 0u);
-        if (ax) posx -= scale_exp2;
-        if (ay) posy -= scale_exp2;
-        if (az) posz -= scale_exp2;
-        t_min = tc_max;
-        idx ^= step_mask;
+        if (!pushed) {
+            // ADVANCE
+            const bool ax = tcorx <= tc_max, ay = tcory <= tc_max, az = tcorz <= tc_max;
+            const uint32_t step_mask = (ax ? 4u : 0u) | (ay ? 2u : 0u) | (az ? 1u : 0u);
+            if (ax) posx -= scale_exp2;
+            if (ay) posy -= scale_exp2;
+            if (az) posz -= scale_exp2;
+            t_min = tc_max;
+            idx ^= step_mask;
 
-        if ((idx & step_mask) != 0u) {
-            // POP
-            uint32_t dbits = 0;
-            if (ax) dbits |= __float_as_uint(posx) ^ __float_as_uint(posx + scale_exp2);
-            if (ay) dbits |= __float_as_uint(posy) ^ __float_as_uint(posy + scale_exp2);
-            if (az) dbits |= __float_as_uint(posz) ^ __float_as_uint(posz + scale_exp2);
-            // esvo.comp:117 takes the exponent of float(dbits); dbits is a union of carry runs of
-            // at most 23 bits inside the cube (exact in binary32), so the index of its highest
-            // set bit is the same number, and anything >= 23 (or dbits == 0) leaves the loop
-            scale = 31u - (uint32_t)__clz((int)dbits);
-            if (scale >= cast_stack_depth) break; // left the cube (also guards the reference's
-                                                  // underflowed stack read, esvo.comp:119-123)
-            scale_exp2 = __uint_as_float((scale - cast_stack_depth + 127u) << 23);
-            const uint32_t level = (cast_stack_depth - 1u) - scale;
-            const uint2 e = level < (uint32_t)LEVELS ? stack[level * BLOCK_THREADS] : make_uint2(0u, 0u);
-            parent = e.x;
-            t_max = __uint_as_float(e.y);
-            const uint32_t shx = __float_as_uint(posx) >> scale, shy = __float_as_uint(posy) >> scale,
-                           shz = __float_as_uint(posz) >> scale;
-            posx = __uint_as_float(shx << scale);
-            posy = __uint_as_float(shy << scale);
-            posz = __uint_as_float(shz << scale);
-            idx = (shx & 1u) * 4u + (shy & 1u) * 2u + (shz & 1u);
-            h = 0.0f;
+            if ((idx & step_mask) != 0u) {
+                // POP
+                uint32_t dbits = 0;
+                if (ax) dbits |= __float_as_uint(posx) ^ __float_as_uint(posx + scale_exp2);
+                if (ay) dbits |= __float_as_uint(posy) ^ __float_as_uint(posy + scale_exp2);
+                if (az) dbits |= __float_as_uint(posz) ^ __float_as_uint(posz + scale_exp2);
+                // esvo.comp:117 takes the exponent of float(dbits); dbits is a union of carry runs
+                // of at most 23 bits inside the cube (exact in binary32), so the index of its
+                // highest set bit is the same number, and anything >= 23 (or dbits == 0) leaves
+                scale = 31u - (uint32_t)__clz((int)dbits);
+                if (scale >= cast_stack_depth) break; // left the cube (also guards the reference's
+                                                      // underflowed stack read, esvo.comp:119-123)
+                scale_exp2 = __uint_as_float((scale - cast_stack_depth + 127u) << 23);
+                const uint32_t level = (cast_stack_depth - 1u) - scale;
+                const uint2 e = level < (uint32_t)LEVELS ? stack_load(stack, level) : make_uint2(0u, 0u);
+                parent = e.x;
+                t_max = __uint_as_float(e.y);
+                const uint32_t shx = __float_as_uint(posx) >> scale, shy = __float_as_uint(posy) >> scale,
+                               shz = __float_as_uint(posz) >> scale;
+                posx = __uint_as_float(shx << scale);
+                posy = __uint_as_float(shy << scale);
+                posz = __uint_as_float(shz << scale);
+                idx = (shx & 1u) * 4u + (shy & 1u) * 2u + (shz & 1u);
+                h = 0.0f;
+            }
         }
         s = load_slot(nodes, parent, idx ^ octant_mask);
     }
@@ -595,7 +622,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) esvo_kernel(const __grid_consta
 // svo_rope (resources/svo_rope.comp:50-153)
 // ---------------------------------------------------------------------------------
 template <bool STATS, bool STRICT>
-__global__ void __launch_bounds__(BLOCK_THREADS) svo_rope_kernel(const __grid_constant__ FrameParams p) {
+__global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_rope_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;

@@ -51,6 +51,9 @@ WORKLOADS = {
 }
 
 
+_JSON_OUT = sys.stdout
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -169,6 +172,11 @@ def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid
 
 # --------------------------------------------------------------------------------------------
 def main():
+    # keep stdout for the ONE JSON line: libraries (NCCL's version banner, torchrun notices)
+    # that print to fd 1 are sent to stderr instead
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=150)
@@ -248,14 +256,17 @@ def main():
         # every rank shades its stripes of the full frame and stores them into rank 0's frame
         ctx.set_target(display, display)
         ctx.set_interleave(n_gpus, rank)
+        # two frames: while rank 0 copies frame i to the host, frame i+1 is stored into the other
         if rank == 0:
-            frame_ptr, handle = ctx.frame_buffer_create(W, H)
-            obj = [handle]
+            made = [ctx.frame_buffer_create(W, H) for _ in range(2)]
+            frame_ptrs = [m[0] for m in made]
+            obj = [[m[1] for m in made]]
         else:
             obj = [None]
         dist.broadcast_object_list(obj, src=0)
         if rank != 0:
-            frame_ptr = ctx.frame_buffer_open(obj[0])
+            frame_ptrs = [ctx.frame_buffer_open(h) for h in obj[0]]
+        frame_ptr = frame_ptrs[0]
         ctx.set_target_buffer(frame_ptr, W)
     else:
         from xenodon_b200 import distributed as xd
@@ -333,6 +344,8 @@ def main():
             ctx.render_download_async(traversal, cam_tuple(cams, warmup + i), pinned[i & 1])
         ctx.sync()
     else:
+        if tile is None:
+            ctx.set_target_buffer(frame_ptrs[0], W)
         for i in range(steps):
             ctx.render(traversal, cam_tuple(cams, warmup + i))
             ctx.sync()
@@ -346,9 +359,15 @@ def main():
                         dst[y:y + g.shape[0]].copy_(g)
                         y += g.shape[0]
             else:
-                dist.barrier()  # every rank's peer stores have landed in rank 0's frame
                 if rank == 0:
-                    pinned[i & 1].array[...] = ctx.frame_buffer_read(frame_ptr, W, H)
+                    ctx.copy_sync()  # frame i-1 is on the host before anyone may overwrite its buffer
+                dist.barrier()  # every rank's peer stores of frame i have landed in rank 0's frame
+                if rank == 0:
+                    ctx.frame_buffer_read_async(frame_ptrs[i & 1], W, H, pinned[i & 1])
+                if i + 1 < steps:
+                    ctx.set_target_buffer(frame_ptrs[(i + 1) & 1], W)
+        if rank == 0 and tile is None:
+            ctx.copy_sync()
     barrier()
     e2e_s = time.perf_counter() - t0
     last_frame = pinned[(steps - 1) & 1].array.copy() if rank == 0 else None
@@ -460,7 +479,7 @@ def main():
         except Exception as e:  # the baseline must never take the GPU number down with it
             result["cpu_baseline"] = {"error": str(e)}
 
-    print(json.dumps(result), flush=True)
+    print(json.dumps(result), file=_JSON_OUT, flush=True)
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -474,7 +493,8 @@ def run_reference_arm(args, wl, traversal, frame, cams, n_gpus):
     W, H = frame
     steps, warmup = args.steps, max(args.warmup, 0)
     if nx * ny * nz > 1100 ** 3:
-        print(json.dumps({"impl": "reference", "unavailable": "host copy of this volume exceeds the arm's budget"}))
+        print(json.dumps({"impl": "reference", "unavailable": "host copy of this volume exceeds the arm's budget"}),
+              file=_JSON_OUT, flush=True)
         return
     log(f"[reference arm] generating {kind_name} {nx}x{ny}x{nz} on the host ...")
     grid = xb.Grid.synthetic(xb.SYNTH_BUNNY if kind_name == "bunny" else xb.SYNTH_TNG, nx, ny, nz, SEED)
@@ -505,7 +525,7 @@ def run_reference_arm(args, wl, traversal, frame, cams, n_gpus):
         "e2e": {"value": round(mr, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(wall, 1),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":

@@ -200,6 +200,12 @@ XN_API int xn_frame_buffer_open(xn_ctx* ctx, const uint8_t handle[64], void** de
 XN_API int xn_frame_buffer_close(xn_ctx* ctx, void* device_ptr);
 XN_API int xn_frame_buffer_read(xn_ctx* ctx, const void* device_ptr, uint32_t w, uint32_t h,
                                 uint32_t* host_dst);
+/* Same, asynchronous on the context's copy stream (host_dst should be pinned, xn_host_alloc):
+ * ordered after the work already enqueued on the context, overlapping later launches.  The
+ * data is valid after xn_copy_sync (or the next xn_sync). */
+XN_API int xn_frame_buffer_read_async(xn_ctx* ctx, const void* device_ptr, uint32_t w, uint32_t h,
+                                      uint32_t* host_dst);
+XN_API int xn_copy_sync(xn_ctx* ctx);
 
 /* ---- host-side data formats (API surface of the path) ---- */
 

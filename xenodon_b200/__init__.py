@@ -106,6 +106,8 @@ _PROTOTYPES = {
     "xn_frame_buffer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "xn_frame_buffer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xn_frame_buffer_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "xn_frame_buffer_read_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "xn_copy_sync": (C.c_int, [C.c_void_p]),
     "xn_tiff_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64 * 3)]),
     "xn_tiff_read": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64]),
     "xn_tiff_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]),
@@ -429,6 +431,18 @@ class PinnedFrame:
             self.array = None
             lib().xn_host_free(self.ptr)
             self.ptr = None
+
+
+def _frame_buffer_read_async(self, ptr: int, w: int, h: int, pinned: "PinnedFrame"):
+    _check(lib().xn_frame_buffer_read_async(self._h, ptr, w, h, pinned.ptr))
+
+
+def _copy_sync(self):
+    _check(lib().xn_copy_sync(self._h))
+
+
+Context.frame_buffer_read_async = _frame_buffer_read_async
+Context.copy_sync = _copy_sync
 
 
 @dataclass

@@ -79,6 +79,7 @@ struct xn_ctx {
     uint64_t pipe_target_px = 0;
     cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool copy_in_flight[2] = {false, false};
+    bool frame_read_in_flight = false;
     int pipe_next = 0;
     double last_ms = 0;
 
@@ -579,9 +580,10 @@ int xn_sync(xn_ctx* ctx, double* kernel_ms) {
         check_ctx(ctx);
         DeviceGuard g(ctx->device);
         XN_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->copy_in_flight[0] || ctx->copy_in_flight[1]) {
+        if (ctx->copy_in_flight[0] || ctx->copy_in_flight[1] || ctx->frame_read_in_flight) {
             XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
             ctx->copy_in_flight[0] = ctx->copy_in_flight[1] = false;
+            ctx->frame_read_in_flight = false;
         }
         if (ctx->timing_pending) {
             float ms = 0;
@@ -774,6 +776,30 @@ int xn_frame_buffer_read(xn_ctx* ctx, const void* device_ptr, uint32_t w, uint32
         DeviceGuard g(ctx->device);
         XN_CUDA(cudaMemcpyAsync(host_dst, device_ptr, (uint64_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
         XN_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int xn_frame_buffer_read_async(xn_ctx* ctx, const void* device_ptr, uint32_t w, uint32_t h, uint32_t* host_dst) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!device_ptr || !host_dst) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        DeviceGuard g(ctx->device);
+        // ordered after everything already enqueued on the context's stream, but executed on
+        // the copy stream so that later traversal launches overlap it
+        XN_CUDA(cudaEventRecord(ctx->ev_rendered[0], ctx->stream));
+        XN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[0], 0));
+        XN_CUDA(cudaMemcpyAsync(host_dst, device_ptr, (uint64_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->frame_read_in_flight = true;
+    });
+}
+
+int xn_copy_sync(xn_ctx* ctx) {
+    return guarded([&] {
+        check_ctx(ctx);
+        DeviceGuard g(ctx->device);
+        XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        ctx->copy_in_flight[0] = ctx->copy_in_flight[1] = false;
+        ctx->frame_read_in_flight = false;
     });
 }
 

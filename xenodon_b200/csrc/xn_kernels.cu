@@ -100,37 +100,80 @@ __device__ __forceinline__ void store_result(const FrameParams& p, uint32_t ix, 
     }
 }
 
-// voxel coordinates of an in-range linear index (x + y*stride_y + z*stride_z)
-__device__ __forceinline__ void recover_position(int32_t idx, int32_t stride_y, int32_t stride_z, int& px, int& py,
-                                                 int& pz) {
-    const uint32_t qz = (uint32_t)idx / (uint32_t)stride_z;
-    const uint32_t rem = (uint32_t)idx - qz * (uint32_t)stride_z;
-    const uint32_t qy = rem / (uint32_t)stride_y;
-    pz = (int)qz;
-    py = (int)qy;
-    px = (int)(rem - qy * (uint32_t)stride_y);
-}
-__device__ __forceinline__ void recover_position(int64_t idx, int64_t stride_y, int64_t stride_z, int& px, int& py,
-                                                 int& pz) {
-    // idx < 2^48: the binary64 quotient estimate is off by at most one, fixed below; the slice
-    // remainder is below 2^32 (dimensions are < 2^16), so the rest is 32-bit arithmetic
-    int64_t qz = (int64_t)((double)idx / (double)stride_z);
-    int64_t rem = idx - qz * stride_z;
-    if (rem < 0) { --qz; rem += stride_z; }
-    else if (rem >= stride_z) { ++qz; rem -= stride_z; }
-    const uint32_t qy = (uint32_t)rem / (uint32_t)stride_y;
-    pz = (int)qz;
-    py = (int)qy;
-    px = (int)((uint32_t)rem - qy * (uint32_t)stride_y);
-}
+// Position of a ray inside the grid as an address.  The voxel coordinates themselves are only
+// tracked in the checked single steps; unchecked segments move the cursor alone and recover the
+// coordinates from it afterwards.
+//   GridCursor<false>: one signed 32-bit voxel index (grids below 2^31 voxels).
+//   GridCursor<true> : a 64-bit pointer to the current z slice plus a 32-bit index inside the
+//                      slice, so that only z steps pay 64-bit arithmetic (2048^3 = 2^33 voxels).
+template <bool BIG>
+struct GridCursor;
+
+template <>
+struct GridCursor<false> {
+    const uint32_t* __restrict__ grid;
+    int32_t idx, dix, diy, diz, stride_y, stride_z;
+    __device__ __forceinline__ GridCursor(const FrameParams& p, int px, int py, int pz, int sx, int sy, int sz)
+        : grid(p.grid), stride_y((int32_t)p.nx), stride_z((int32_t)(p.nx * p.ny)) {
+        dix = sx;
+        diy = sy * stride_y;
+        diz = sz * stride_z;
+        idx = px + py * stride_y + pz * stride_z;
+    }
+    __device__ __forceinline__ void step_x() { idx += dix; }
+    __device__ __forceinline__ void step_y() { idx += diy; }
+    __device__ __forceinline__ void step_z() { idx += diz; }
+    __device__ __forceinline__ uint32_t load() const { return __ldg(grid + idx); }
+    // voxel coordinates of the (in-range) cursor
+    __device__ __forceinline__ void recover(int& px, int& py, int& pz) const {
+        const uint32_t qz = (uint32_t)idx / (uint32_t)stride_z;
+        const uint32_t rem = (uint32_t)idx - qz * (uint32_t)stride_z;
+        const uint32_t qy = rem / (uint32_t)stride_y;
+        pz = (int)qz;
+        py = (int)qy;
+        px = (int)(rem - qy * (uint32_t)stride_y);
+    }
+};
+
+template <>
+struct GridCursor<true> {
+    const uint32_t* __restrict__ grid;
+    const uint32_t* slice; // grid + pz * stride_z (may point outside the grid while out of range)
+    int64_t diz, stride_z;
+    int32_t ixy, dix, diy, stride_y;
+    __device__ __forceinline__ GridCursor(const FrameParams& p, int px, int py, int pz, int sx, int sy, int sz)
+        : grid(p.grid), stride_z((int64_t)p.nx * (int64_t)p.ny), stride_y((int32_t)p.nx) {
+        dix = sx;
+        diy = sy * stride_y;
+        diz = (int64_t)sz * stride_z;
+        ixy = px + py * stride_y;
+        slice = grid + (int64_t)pz * stride_z;
+    }
+    __device__ __forceinline__ void step_x() { ixy += dix; }
+    __device__ __forceinline__ void step_y() { ixy += diy; }
+    __device__ __forceinline__ void step_z() { slice += diz; }
+    __device__ __forceinline__ uint32_t load() const { return __ldg(slice + ixy); }
+    __device__ __forceinline__ void recover(int& px, int& py, int& pz) const {
+        // slice offset < 2^48: the binary64 quotient is off by at most one, fixed below
+        const int64_t off = (int64_t)(slice - grid);
+        int64_t qz = (int64_t)((double)off / (double)stride_z);
+        const int64_t rem = off - qz * stride_z;
+        if (rem < 0) --qz;
+        else if (rem >= stride_z) ++qz;
+        const uint32_t qy = (uint32_t)ixy / (uint32_t)stride_y;
+        pz = (int)qz;
+        py = (int)qy;
+        px = (int)((uint32_t)ixy - qy * (uint32_t)stride_y);
+    }
+};
 
 // ---------------------------------------------------------------------------------
 // DDA (resources/dda.comp:13-73)
-// IdxT: int32_t for grids below 2^31 voxels, int64_t beyond (2048^3 = 2^33 voxels).
-// The texel of the NEXT step is requested before the current one is accumulated (its address
-// never depends on loaded data), so every warp overlaps its own load latency with arithmetic.
+// BIG selects the addressing of grids of 2^31 voxels and more (GridCursor).
+// Texels are requested ahead of their accumulation (their addresses never depend on loaded
+// data), so every warp overlaps its own load latency with arithmetic.
 // ---------------------------------------------------------------------------------
-template <bool STATS, bool STRICT, typename IdxT>
+template <bool STATS, bool STRICT, bool BIG>
 __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
@@ -164,15 +207,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
         float sdy = (sg.y * ((floorf(ro.y) - ro.y) + 0.5f) + 0.5f) * tdy;
         float sdz = (sg.z * ((floorf(ro.z) - ro.z) + 0.5f) + 0.5f) * tdz;
 
-        const IdxT stride_y = (IdxT)p.nx, stride_z = (IdxT)p.nx * (IdxT)p.ny;
-        const IdxT dix = (IdxT)sx, diy = (IdxT)sy * stride_y, diz = (IdxT)sz * stride_z;
-        IdxT idx = (IdxT)px + (IdxT)py * stride_y + (IdxT)pz * stride_z;
-        const uint32_t* __restrict__ grid = p.grid;
+        GridCursor<BIG> cur(p, px, py, pz, sx, sy, sz);
 
         // texelFetch; outside the grid -> 0 (border)
         bool inr = (uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz;
         uint32_t v = 0;
-        if (inr) v = __ldg(grid + idx);
+        if (inr) v = cur.load();
 
         float t = 0.0f;
         const float t_end = t_max - t_min;
@@ -208,19 +248,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
         const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0; \
         DT = t0 - t;                                               \
         t = t0;                                                    \
-        if (mx) { sdx += tdx; idx += dix; }                        \
-        if (my) { sdy += tdy; idx += diy; }                        \
-        if (mz) { sdz += tdz; idx += diz; }                        \
+        if (mx) { sdx += tdx; cur.step_x(); }                      \
+        if (my) { sdy += tdy; cur.step_y(); }                      \
+        if (mz) { sdz += tdz; cur.step_z(); }                      \
         st.step();                                                 \
         st.read(4);                                                \
     }
 #define XN_DDA_TRIP(N, P)                                                        \
     {                                                                            \
         float d0;                                                                \
-        XN_DDA_STEP(d0) N##0 = __ldg(grid + idx);                                \
-        XN_DDA_STEP(N##d1) N##1 = __ldg(grid + idx);                             \
-        XN_DDA_STEP(N##d2) N##2 = __ldg(grid + idx);                             \
-        XN_DDA_STEP(N##d3) N##3 = __ldg(grid + idx);                             \
+        XN_DDA_STEP(d0) N##0 = cur.load();                                        \
+        XN_DDA_STEP(N##d1) N##1 = cur.load();                                     \
+        XN_DDA_STEP(N##d2) N##2 = cur.load();                                     \
+        XN_DDA_STEP(N##d3) N##3 = cur.load();                                     \
         acc.add(P##0, P##d1);                                                    \
         acc.add(P##1, P##d2);                                                    \
         acc.add(P##2, P##d3);                                                    \
@@ -254,13 +294,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
                         while (t < t_lim) {
                             float dt;
                             XN_DDA_STEP(dt)
-                            const uint32_t vn = __ldg(grid + idx);
+                            const uint32_t vn = cur.load();
                             acc.add(v, dt);
                             v = vn;
                         }
 #undef XN_DDA_STEP
                         // recover the voxel coordinates from the linear index (still in range)
-                        recover_position(idx, stride_y, stride_z, px, py, pz);
+                        cur.recover(px, py, pz);
                         continue;
                     }
                 }
@@ -275,13 +315,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
             const bool mz = sdz == t0;
             const float dt = t0 - t;
             t = t0;
-            if (mx) { sdx += tdx; px += sx; idx += dix; }
-            if (my) { sdy += tdy; py += sy; idx += diy; }
-            if (mz) { sdz += tdz; pz += sz; idx += diz; }
+            if (mx) { sdx += tdx; px += sx; cur.step_x(); }
+            if (my) { sdy += tdy; py += sy; cur.step_y(); }
+            if (mz) { sdz += tdz; pz += sz; cur.step_z(); }
 
             inr = (uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz;
             uint32_t vn = 0; // texel of the next step (used only if the loop continues)
-            if (inr) vn = __ldg(grid + idx);
+            if (inr) vn = cur.load();
 
             acc.add(v, dt);
             v = vn;
@@ -712,9 +752,9 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
         case 0:
             // XN_FORCE_IDX64=1 (test knob) runs the 64-bit-index kernel on small grids too
             if ((uint64_t)p.nx * p.ny * p.nz < (1ull << 31) && !force_idx64())
-                dda_kernel<STATS, STRICT, int32_t><<<grid, block, 0, stream>>>(p);
+                dda_kernel<STATS, STRICT, false><<<grid, block, 0, stream>>>(p);
             else
-                dda_kernel<STATS, STRICT, int64_t><<<grid, block, 0, stream>>>(p);
+                dda_kernel<STATS, STRICT, true><<<grid, block, 0, stream>>>(p);
             break;
         case 1: svo_naive_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p); break;
         case 2:

@@ -73,6 +73,11 @@ typedef struct xn_render_stats {
 
 typedef struct xn_ctx xn_ctx;
 
+/* ConstructionStats, src/model/OctreeConstruction.h:50-63 */
+typedef struct xn_build_stats {
+    uint64_t total_leaves, unique_leaves, total_nodes, depth;
+} xn_build_stats;
+
 XN_API const char* xn_last_error(void);
 XN_API const char* xn_version(void);
 XN_API int xn_traversal_from_name(const char* shader_name); /* <0 if unknown */
@@ -100,6 +105,14 @@ XN_API int xn_upload_svo(xn_ctx* ctx, const xn_node* nodes, uint64_t count, uint
 /* same, from memory already resident on ctx's device (copied device-to-device) */
 XN_API int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t ny, uint64_t nz);
 XN_API int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uint64_t side);
+/* `xenodon convert --chan-diff n [--rope]` on the GPU, from the grid resident on ctx
+ * (build_octree, src/model/OctreeConstruction.h:226-237; Octree::generate_ropes,
+ * src/model/Octree.cpp:181-201).  The node array is byte-identical to the host builder's
+ * (xn_build_octree) and so to the reference's.  type: 0 sparse, 2 rope (--dag and --std-dev are
+ * host-only).  nodes_out (nullable) receives a host copy (release with xn_free); bind != 0 also
+ * makes the tree the context's resident octree, without a host round trip. */
+XN_API int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_node** nodes_out,
+                                    uint64_t* count_out, uint64_t* side_out, xn_build_stats* stats_out);
 /* deterministic synthetic volumes generated directly in device memory
  * (BASELINE.md section 4): kind 0 = "bunny-CT", 1 = "TNG gas"; bound as the grid */
 XN_API int xn_synth_grid_device(xn_ctx* ctx, int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t seed);
@@ -225,9 +238,6 @@ XN_API int xn_svo_write(const char* path, const xn_node* nodes, uint64_t count, 
 /* build_octree, src/model/OctreeConstruction.h:226-237 (`xenodon convert`).
  * heuristic 0 = --chan-diff (param 0..255), 1 = --std-dev; type 0 sparse, 1 dag, 2 rope.
  * *nodes_out is allocated by the library; release with xn_free. */
-typedef struct xn_build_stats {
-    uint64_t total_leaves, unique_leaves, total_nodes, depth;
-} xn_build_stats;
 XN_API int xn_build_octree(const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz, int heuristic,
                            double param, int type, xn_node** nodes_out, uint64_t* count_out,
                            uint64_t* side_out, xn_build_stats* stats_out);

@@ -1,0 +1,69 @@
+"""`xenodon convert` on the GPU (xn_convert_resident_grid): the node array must be byte-identical
+to the host builder's (itself pinned against the reference's own code), for sparse and rope
+trees, any threshold, grids that are not powers of two, and through to rendering."""
+import numpy as np
+import pytest
+
+from util import CAMERAS, blobby_grid, random_grid
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_convert(xb, g, **kw):
+    ctx = xb.Context(0)
+    try:
+        ctx.upload_grid(xb.Grid(g))
+        return ctx.convert_resident_grid(want_nodes=True, bind=False, **kw)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 2, 2), (3, 3, 3), (8, 8, 8), (16, 11, 16), (20, 9, 5), (40, 33, 17),
+                                  (64, 64, 64), (33, 70, 12)])
+def test_gpu_convert_matches_host_builder(xb, dims):
+    rng = np.random.default_rng(sum(dims) * 7 + 1)
+    grids = [random_grid(rng, *dims, quant=64), blobby_grid(rng, *dims), np.full((dims[2], dims[1], dims[0], 4), 77, np.uint8),
+             rng.integers(0, 256, (dims[2], dims[1], dims[0], 4), dtype=np.uint8)]
+    for g in grids:
+        for ttype in (xb.TYPE_SPARSE, xb.TYPE_ROPE):
+            for thr in (0, 60, 255):
+                tree, st, count, side = _gpu_convert(xb, g, chan_diff=thr, type=ttype)
+                ref, rst = xb.build_octree(xb.Grid(g), chan_diff=thr, type=ttype)
+                assert (count, side) == (len(ref.nodes), ref.side)
+                assert tree.nodes.tobytes() == ref.nodes.tobytes(), (dims, ttype, thr)
+                assert st == rst, (dims, ttype, thr, st, rst)
+
+
+def test_gpu_convert_synthetic_volumes_and_render(xb, xo):
+    """Device-generated volume -> GPU convert -> bound octree -> every SVO traversal == oracle on the
+    host-built tree of the host-generated (bit-identical) volume."""
+    for kind, dims in ((xb.SYNTH_BUNNY, (96, 68, 96)), (xb.SYNTH_TNG, (128, 128, 128))):
+        host = xb.Grid.synthetic(kind, *dims)
+        ref, rst = xb.build_octree(host, chan_diff=0, type=xb.TYPE_ROPE)
+        ctx = xb.Context(0)
+        ctx.synth_grid(kind, *dims)
+        tree, st, count, side = ctx.convert_resident_grid(chan_diff=0, type=xb.TYPE_ROPE, bind=True, want_nodes=True)
+        assert tree.nodes.tobytes() == ref.nodes.tobytes() and st == rst
+        ctx.set_precision(True)
+        ctx.set_target((0, 0, 160, 90))
+        ctx.set_params((1, 1, 1), None, 4.0)
+        for t in ("svo-naive", "svo-df", "esvo", "svo-rope"):
+            ctx.render(t, CAMERAS["orbit"])
+            ctx.sync()
+            img = ctx.download()
+            want = xo.render(t, nodes=ref.nodes, side=ref.side, camera=CAMERAS["orbit"], output=(0, 0, 160, 90),
+                             emission=4.0, want_stats=False)[0]
+            assert np.array_equal(img, want), t
+        ctx.close()
+
+
+def test_gpu_convert_rejects_host_only_options(xb):
+    ctx = xb.Context(0)
+    ctx.upload_grid(xb.Grid(np.zeros((4, 4, 4, 4), np.uint8)))
+    with pytest.raises(xb.XenodonError, match="--dag is host-only"):
+        ctx.convert_resident_grid(type=xb.TYPE_DAG)
+    ctx.close()
+    ctx = xb.Context(0)
+    with pytest.raises(xb.XenodonError, match="no grid is resident"):
+        ctx.convert_resident_grid()
+    ctx.close()

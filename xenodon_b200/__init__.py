@@ -78,6 +78,8 @@ _PROTOTYPES = {
     "xn_upload_svo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "xn_upload_grid_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "xn_upload_svo_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "xn_convert_resident_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(BuildStats)]),
     "xn_synth_grid_device": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]),
     "xn_synth_grid_host": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "xn_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -315,6 +317,24 @@ class Context:
         out = np.empty((nz, ny, nx, 4), dtype=np.uint8)
         _check(lib().xn_download_grid(self._h, out.ctypes.data, out.nbytes))
         return Grid(out)
+
+    def convert_resident_grid(self, chan_diff: int = 0, type: int = TYPE_SPARSE, bind: bool = True,
+                              want_nodes: bool = False):
+        """GPU `xenodon convert` of the resident grid -> (Octree | None, stats dict, count, side)."""
+        out, count, side, st = C.c_void_p(), C.c_uint64(), C.c_uint64(), BuildStats()
+        _check(lib().xn_convert_resident_grid(self._h, chan_diff, type, int(bind),
+                                              C.byref(out) if want_nodes else None, C.byref(count), C.byref(side),
+                                              C.byref(st)))
+        tree = None
+        if want_nodes:
+            try:
+                buf = (C.c_char * (count.value * 40)).from_address(out.value)
+                tree = Octree(np.frombuffer(buf, dtype=NODE_DTYPE).copy(), side.value)
+            finally:
+                lib().xn_free(out)
+        if bind:
+            self.model_dim = (side.value,) * 3
+        return tree, {k: getattr(st, k) for k, _ in BuildStats._fields_}, count.value, side.value
 
     def upload_svo(self, tree: Octree):
         _check(lib().xn_upload_svo(self._h, tree.nodes.ctypes.data, len(tree.nodes), tree.side))

@@ -12,6 +12,7 @@
 
 #include "host/xn_host.hpp"
 #include "xenodon_b200.h"
+#include "xn_convert.h"
 #include "xn_kernels.h"
 
 namespace {
@@ -360,6 +361,43 @@ int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uin
         if (count > 0xFFFFFFFFull) throw xn::Error(XN_ERR_LIMIT, "octree exceeds 2^32 - 1 nodes");
         DeviceGuard g(ctx->device);
         finish_svo_upload(ctx, const_cast<void*>(d_nodes40), count, side);
+    });
+}
+
+int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_node** nodes_out, uint64_t* count_out,
+                             uint64_t* side_out, xn_build_stats* stats_out) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!ctx->grid) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
+        if (chan_diff < 0 || chan_diff > 255) throw xn::Error(XN_ERR_INVALID, "channel difference must be 0..255");
+        if (type != 0 && type != 2)
+            throw xn::Error(XN_ERR_INVALID, "the GPU builder makes sparse (0) and rope (2) trees; --dag is host-only");
+        if (nodes_out) *nodes_out = nullptr;
+        DeviceGuard g(ctx->device);
+        void* d_nodes = nullptr;
+        uint64_t count = 0, side = 0;
+        xn::gpu_build_octree(ctx->grid, ctx->nx, ctx->ny, ctx->nz, (uint32_t)chan_diff, type == 2, ctx->stream, &d_nodes,
+                             &count, &side, stats_out);
+        try {
+            if (nodes_out) {
+                xn_node* host = (xn_node*)std::malloc(std::max<uint64_t>(count, 1) * sizeof(xn_node));
+                if (!host) throw std::bad_alloc();
+                cudaError_t e = cudaMemcpyAsync(host, d_nodes, count * sizeof(xn_node), cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) {
+                    std::free(host);
+                    throw CudaError{e, "cudaMemcpyAsync (octree nodes)"};
+                }
+                *nodes_out = host;
+            }
+            if (bind) finish_svo_upload(ctx, d_nodes, count, side);
+        } catch (...) {
+            cudaFree(d_nodes);
+            throw;
+        }
+        cudaFree(d_nodes);
+        if (count_out) *count_out = count;
+        if (side_out) *side_out = side;
     });
 }
 

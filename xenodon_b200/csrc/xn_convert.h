@@ -1,0 +1,15 @@
+// xn_convert.h -- GPU octree construction (xn_convert.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "xenodon_b200.h"
+
+namespace xn {
+// Builds the octree of an RGBA8 grid resident on the current device.  *d_nodes_out receives a
+// cudaMalloc'ed array of *count_out 40-byte nodes (the .svo node array, node 0 = root).
+void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t chan_diff, bool rope,
+                      cudaStream_t stream, void** d_nodes_out, uint64_t* count_out, uint64_t* side_out,
+                      xn_build_stats* stats_out);
+} // namespace xn

@@ -44,8 +44,12 @@ WORKLOADS = {
                  desc="ESVO, V-bunny 512x361x512 as lossless SVO (convert --chan-diff 0), 1920x1080, camera.txt path"),
     "cfg3": dict(volume=("tng", 1024, 1024, 1024), frame=(3840, 2160), camera="camera", traversal="dda",
                  desc="DDA, V-tng 1024^3 RGBA8 grid (4 GiB), 3840x2160, camera.txt path"),
+    "cfg3r": dict(volume=("tng", 1024, 1024, 1024), frame=(3840, 2160), camera="camera", traversal="svo-rope",
+                  desc="svo-rope, V-tng 1024^3 as lossless rope SVO (GPU convert --chan-diff 0 --rope), 3840x2160, camera.txt path"),
     "cfg4": dict(volume=("tng", 2048, 2048, 2048), frame=(3840, 2160), camera="camera", traversal="dda",
                  desc="DDA, V-tng 2048^3 RGBA8 grid (32 GiB), 3840x2160, camera.txt path"),
+    "cfg4e": dict(volume=("tng", 2048, 2048, 2048), frame=(3840, 2160), camera="camera", traversal="esvo",
+                  desc="ESVO, V-tng 2048^3 as lossless SVO (GPU convert --chan-diff 0), 3840x2160, camera.txt path"),
     "cfg5": dict(volume=("tng", 1024, 1024, 1024), frame=(7680, 4320), camera="camera-rotate", traversal="dda",
                  desc="DDA, V-tng 1024^3, 7680x4320 split by screen region, camera-rotate"),
 }
@@ -230,22 +234,22 @@ def main():
     tree = None
     need_tree = traversal != "dda"
     extras = [] if args.no_extras or n_gpus > 1 or args.workload != "cfg2" else ["dda", "svo-rope", "svo-df", "svo-naive"]
+    tree_side = None
+    want_host = (n_gpus == 1 and not args.no_extras and rank == 0)  # the CPU baseline needs host copies
     if need_tree or extras:
-        host_grid = ctx.download_grid()
         rope = traversal == "svo-rope" or "svo-rope" in extras
+        # `xenodon convert --chan-diff 0 [--rope]` on the GPU, from the resident grid (byte-identical
+        # to the host builder); the node array comes back to the host only for the CPU baseline
+        tree, bstats, n_nodes, tree_side = ctx.convert_resident_grid(
+            chan_diff=0, type=xb.TYPE_ROPE if rope else xb.TYPE_SPARSE, bind=True, want_nodes=want_host)
         if rank == 0:
-            log(f"[bench] building the SVO of {nx}x{ny}x{nz} on the host (convert --chan-diff 0"
-                f"{' --rope' if rope else ''}) ...")
-        tree, bstats = xb.build_octree(host_grid, chan_diff=0, type=xb.TYPE_ROPE if rope else xb.TYPE_SPARSE)
-        ctx.upload_svo(tree)
-        if rank == 0:
-            log(f"[bench] SVO: {len(tree.nodes)} nodes, side {tree.side}, depth {bstats['depth']}, "
-                f"{len(tree.nodes) * 64 / 2**20:.0f} MiB resident")
+            log(f"[bench] SVO (GPU convert --chan-diff 0{' --rope' if rope else ''}): {n_nodes} nodes, side "
+                f"{tree_side}, depth {bstats['depth']}, {n_nodes * 64 / 2**20:.0f} MiB resident")
     if rank == 0:
         log(f"[bench] setup {time.perf_counter() - t_setup:.1f} s; frame {W}x{H}, traversal {traversal}, N={n_gpus}")
 
     display = (0, 0, W, H)
-    ctx.set_params((1, 1, 1), (nx, ny, nz) if traversal == "dda" else (tree.side,) * 3, EMISSION)
+    ctx.set_params((1, 1, 1), (nx, ny, nz) if traversal == "dda" else (tree_side,) * 3, EMISSION)
 
     # ---- partition + gather plumbing ----
     frame_ptr = None
@@ -443,7 +447,7 @@ def main():
     for t in extras:
         if t == traversal:
             continue
-        ctx.set_params((1, 1, 1), (nx, ny, nz) if t == "dda" else (tree.side,) * 3, EMISSION)
+        ctx.set_params((1, 1, 1), (nx, ny, nz) if t == "dda" else (tree_side,) * 3, EMISSION)
         for i in range(3):
             ctx.render(t, cam_tuple(cams, i))
         ctx.sync()
@@ -459,8 +463,12 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample ----
     if n_gpus == 1 and not args.no_extras:
         try:
-            if host_grid is None:
+            if traversal == "dda":
+                if nx * ny * nz * 4 > (8 << 30):
+                    raise RuntimeError("volume too large for the host-side baseline sample")
                 host_grid = ctx.download_grid()
+            else:
+                host_grid = xb.Grid(np.zeros((1, 1, 1, 4), np.uint8))  # unused by the octree traversals
             sample_steps = max(1, min(steps, 12))
             sub = cams[np.linspace(0, len(cams) - 1, sample_steps).astype(int)] if len(cams) > 1 else cams
             mr, info = run_oracle_frames(args.workload, traversal, (W, H), sub, sample_steps, 1,

@@ -124,6 +124,16 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
+def measured_traffic(workload, kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            e = json.load(f).get(f"{workload}/{kernel_name}")
+        return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]) if e else None
+    except Exception:
+        return None
+
+
 def load_cameras(name):
     from xenodon_b200 import cameras
     return cameras.SCRIPTS[name]()
@@ -146,9 +156,14 @@ def oracle_sample_rows(h, bands=8, rows_per_band=8):
     return out
 
 
-def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid, tree):
-    """Times the oracle on a bounded sample of each frame; returns (Mrays/s, info)."""
-    from oracle import xo
+def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid, tree, prefer_ref=False):
+    """Times the CPU implementation on a bounded sample of each frame; returns (Mrays/s, info).
+
+    prefer_ref: use oracle/_ref/libxnref_glsl.so -- the reference's OWN shader text compiled as
+    C++ (built where the reference checkout existed; it travels with the repo) -- when present
+    (kind "reference"); otherwise the C restatement oracle/xn_oracle.c (kind "port")."""
+    from oracle import xo, xref
+    use_ref = prefer_ref and xref.available()
     W, H = frame
     bands = oracle_sample_rows(H)
     threads = os.cpu_count() or 1
@@ -158,12 +173,16 @@ def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid
         cam = cam_tuple(cams, i)
         t0 = time.perf_counter()
         for (y0, rows) in bands:
-            kw = dict(camera=cam, output=(0, y0, W, rows), display=(0, 0, W, H), emission=EMISSION,
-                      threads=threads, want_stats=False)
-            if traversal == "dda":
-                xo.render("dda", grid=host_grid, **kw)
+            kw = dict(camera=cam, output=(0, y0, W, rows), display=(0, 0, W, H), emission=EMISSION)
+            if use_ref:
+                if traversal == "dda":
+                    xref.render("dda", grid=host_grid, **kw)
+                else:
+                    xref.render(traversal, nodes=tree.nodes, side=tree.side, **kw)
+            elif traversal == "dda":
+                xo.render("dda", grid=host_grid, threads=threads, want_stats=False, **kw)
             else:
-                xo.render(traversal, nodes=tree.nodes, side=tree.side, **kw)
+                xo.render(traversal, nodes=tree.nodes, side=tree.side, threads=threads, want_stats=False, **kw)
         dt = time.perf_counter() - t0
         if i >= warmup:
             t_total += dt
@@ -171,7 +190,8 @@ def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid
     mrays = rays / t_total / 1e6
     sample = (f"{steps} frames x {len(bands)} bands of {bands[0][1]} rows ({sum(r for _, r in bands)}/{H} rows "
               f"of each {W}x{H} frame), all {threads} host threads")
-    return mrays, dict(cores=threads, sample=sample, seconds=t_total, rays=rays)
+    return mrays, dict(cores=threads, sample=sample, seconds=t_total, rays=rays,
+                       kind="reference" if use_ref else "port")
 
 
 # --------------------------------------------------------------------------------------------
@@ -432,7 +452,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 1), "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None,
+                     "traffic": measured_traffic(args.workload, kernel_name) if n_gpus == 1 else None,
+                     "traffic_source": "profiles/traffic.json (ncu --set full capture of camera frame 3)",
                      "algorithmic_bytes_per_launch": round(alg_bytes_per_frame),
                      "steps_per_launch": round(alg_steps_per_frame),
                      "mean_kernel_ms": round(mean_kernel_ms, 5),
@@ -474,7 +495,7 @@ def main():
             mr, info = run_oracle_frames(args.workload, traversal, (W, H), sub, sample_steps, 1,
                                          host_grid.data, tree)
             result["cpu_baseline"] = {"value": round(mr, 3), "unit": "Mrays/s", "cores": info["cores"],
-                                      "kind": "port", "sample": info["sample"]}
+                                      "kind": info["kind"], "sample": info["sample"]}
             # parity spot check of the last e2e frame against the oracle (not timed)
             from oracle import xo
             cam = cam_tuple(cams, warmup + steps - 1)
@@ -515,7 +536,8 @@ def run_reference_arm(args, wl, traversal, frame, cams, n_gpus):
     idx = np.linspace(warmup, warmup + steps - 1, n).astype(int)
     sub = cams[[i % len(cams) for i in idx]]
     t0 = time.perf_counter()
-    mr, info = run_oracle_frames(args.workload, traversal, (W, H), sub, n, min(warmup, 1), grid.data, tree)
+    mr, info = run_oracle_frames(args.workload, traversal, (W, H), sub, n, min(warmup, 1), grid.data, tree,
+                                 prefer_ref=True)
     wall = time.perf_counter() - t0
     rows = sum(r for _, r in oracle_sample_rows(H))
     line = {
@@ -526,9 +548,10 @@ def run_reference_arm(args, wl, traversal, frame, cams, n_gpus):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "traversal": traversal, "frame": f"{W}x{H}",
                    "volume": f"{kind_name} {nx}x{ny}x{nz} seed {SEED}", "camera": wl["camera"],
                    "emission": EMISSION,
-                   "note": "reference Vulkan build cannot run in this image (no loader/ICD/glslc); this arm times "
-                           "the CPU restatement of its shaders (oracle/xn_oracle.c, pinned against the shader text)"},
-        "cpu_baseline": {"value": round(mr, 3), "unit": "Mrays/s", "cores": info["cores"], "kind": "port",
+                   "note": "the reference's Vulkan build cannot run in this image (no loader/ICD/glslc); this arm "
+                           "times its compute-shader text compiled as C++ (oracle/_ref, kind 'reference') or, where "
+                           "that library is absent, the C restatement oracle/xn_oracle.c (kind 'port')"},
+        "cpu_baseline": {"value": round(mr, 3), "unit": "Mrays/s", "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
         "e2e": {"value": round(mr, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(wall, 1),

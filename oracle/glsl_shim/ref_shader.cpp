@@ -61,7 +61,7 @@ extern "C" int XN_CAT(xnref_render_, XN_NS)(const xnref_args* a) {
 
     // dispatch: ceil(extent / 8) workgroups of 8x8 (src/render/Renderer.cpp:74,89)
     const int64_t gx = ((int64_t)a->out_w - 1) / 8 + 1, gy = ((int64_t)a->out_h - 1) / 8 + 1;
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
     for (int64_t wy = 0; wy < gy; ++wy)
         for (int64_t wx = 0; wx < gx; ++wx)
             for (uint32_t ly = 0; ly < 8; ++ly)

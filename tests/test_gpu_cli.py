@@ -51,8 +51,14 @@ def test_render_headless_tiff_and_svo(xb, xo, tmp_path):
 
     # convert + every SVO traversal, --repeat, --discard-output
     svo, rope = tmp_path / "vol.svo", tmp_path / "vol-rope.svo"
-    run(xb, "convert", tif, svo)
-    run(xb, "convert", "--rope", tif, rope)
+    assert "Built on the GPU" in run(xb, "convert", tif, svo)
+    assert "Built on the GPU" in run(xb, "convert", "--rope", tif, rope)
+    # the host builder writes the same bytes
+    for flags, path in (([], svo), (["--rope"], rope)):
+        host = tmp_path / "host.svo"
+        assert "Built on the host" in run(xb, "convert", "--host", *flags, tif, host)
+        assert host.read_bytes() == path.read_bytes()
+    assert "Built on the host" in run(xb, "convert", "--dag", tif, tmp_path / "dag.svo")
     for shader, path in (("svo-naive", svo), ("svo-df", svo), ("esvo", svo), ("svo-rope", rope)):
         out = run(xb, "render", "--headless", conf, path, "-s", shader, "--camera", cam, "--repeat", "2",
                   "--discard-output", "--stats-output", stats, "-e", "4")

@@ -267,7 +267,9 @@ const char* HELP_CONVERT =
     "                     --dag and --rope are mutually exclusive.\n"
     "  --chan-diff <n>    Split a region while any channel differs by more than n (0..255). Default 0.\n"
     "  --std-dev <x>      Split a region while its standard deviation exceeds x (>= 0).\n"
-    "                     --chan-diff and --std-dev are mutually exclusive.\n";
+    "                     --chan-diff and --std-dev are mutually exclusive.\n"
+    "  --host             Build on the host even when a CUDA device is present (the GPU builder\n"
+    "                     handles --chan-diff sparse/rope trees and writes identical files).\n";
 const char* HELP_SYSINFO = "Usage: xenodon sysinfo\n\nLists CUDA devices; the index shown is the 'vkindex' of a headless configuration.\n";
 const char* HELP_HEADLESS =
     "The headless configuration consists of one or more blocks:\n"
@@ -613,11 +615,11 @@ void render(const std::vector<const char*>& args) {
 // ---------------------------------------------------------------------------------
 void convert(const std::vector<const char*>& args) {
     std::string src, dst;
-    bool dag = false, rope = false;
+    bool dag = false, rope = false, host_only = false;
     int channel_difference = -1;
     double stddev = -1;
     Command cmd;
-    cmd.flags = {{&dag, "--dag"}, {&rope, "--rope"}};
+    cmd.flags = {{&dag, "--dag"}, {&rope, "--rope"}, {&host_only, "--host"}};
     cmd.parameters = {{int_range_opt<int>(&channel_difference, 0, 255), "channel difference", "--chan-diff"},
                       {float_min_opt<double>(&stddev, 0.0), "std. dev", "--std-dev"}};
     cmd.positional = {{string_opt(&src), "source tiff path"}, {string_opt(&dst), "destination svo path"}};
@@ -660,14 +662,30 @@ void convert(const std::vector<const char*>& args) {
     uint64_t count = 0, side = 0;
     xn_build_stats st{};
     const int type = dag ? 1 : rope ? 2 : 0;
-    const int rc = stddev >= 0
-                       ? xn_build_octree(grid.data(), dims[0], dims[1], dims[2], 1, stddev, type, &nodes, &count, &side, &st)
-                       : xn_build_octree(grid.data(), dims[0], dims[1], dims[2], 0,
-                                         (double)std::max(channel_difference, 0), type, &nodes, &count, &side, &st);
+    // The GPU builder (byte-identical output) handles --chan-diff for sparse and rope trees; --dag,
+    // --std-dev, --host, or the absence of a CUDA device use the host builder.
+    int rc = XN_ERR_INVALID;
+    bool on_gpu = false;
+    int n_devices = 0;
+    if (!host_only && stddev < 0 && !dag && xn_device_count(&n_devices) == XN_OK && n_devices > 0) {
+        xn_ctx* ctx = nullptr;
+        if (xn_ctx_create(0, &ctx) == XN_OK) {
+            if (xn_upload_grid(ctx, grid.data(), dims[0], dims[1], dims[2]) == XN_OK)
+                rc = xn_convert_resident_grid(ctx, std::max(channel_difference, 0), type, 0, &nodes, &count, &side, &st);
+            xn_ctx_destroy(ctx);
+            on_gpu = rc == XN_OK;
+        }
+    }
+    if (!on_gpu)
+        rc = stddev >= 0
+                 ? xn_build_octree(grid.data(), dims[0], dims[1], dims[2], 1, stddev, type, &nodes, &count, &side, &st)
+                 : xn_build_octree(grid.data(), dims[0], dims[1], dims[2], 0, (double)std::max(channel_difference, 0),
+                                   type, &nodes, &count, &side, &st);
     if (rc != XN_OK) {
         std::printf("Error: %s\n", xn_last_error());
         return;
     }
+    std::printf("Built on the %s\n", on_gpu ? "GPU" : "host");
     {
         // same arithmetic as the reference's report (src/convert.cpp:86-111), quirks included
         auto ipow = [](size_t x, size_t y) {

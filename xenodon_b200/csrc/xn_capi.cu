@@ -90,6 +90,7 @@ struct xn_ctx {
     xn::DNode* nodes = nullptr;
     uint64_t node_count = 0, side = 0;
     uint32_t root_meta = 0, max_depth = 0;
+    bool grid_has_black_background = false;
 
     // target
     xn_rect output{0, 0, 0, 0}, display{0, 0, 0, 0};
@@ -174,6 +175,22 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.max_depth = ctx->max_depth;
     p.il_count = ctx->il_count;
     p.il_index = ctx->il_index;
+    p.skip_empty = ctx->grid_has_black_background ? 1u : 0u;
+}
+
+// after a grid became resident: does it have a black background worth skipping (>= 25 % black)?
+void classify_grid(xn_ctx* ctx) {
+    const uint64_t n = ctx->nx * ctx->ny * ctx->nz;
+    unsigned long long* d = nullptr;
+    XN_CUDA(cudaMalloc(&d, 16));
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemsetAsync(d, 0, 16, ctx->stream);
+    if (e == cudaSuccess) e = xn::launch_count_black(ctx->grid, n, n > (1ull << 24) ? 61 : 1, d, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) throw CudaError{e, "classify_grid"};
+    ctx->grid_has_black_background = h[1] > 0 && h[0] * 4 >= h[1];
 }
 
 void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) {
@@ -312,6 +329,7 @@ int xn_upload_grid(xn_ctx* ctx, const uint8_t* rgba, uint64_t nx, uint64_t ny, u
         ctx->nx = nx;
         ctx->ny = ny;
         ctx->nz = nz;
+        classify_grid(ctx);
     });
 }
 
@@ -329,6 +347,7 @@ int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t
         ctx->nx = nx;
         ctx->ny = ny;
         ctx->nz = nz;
+        classify_grid(ctx);
     });
 }
 
@@ -416,6 +435,7 @@ int xn_synth_grid_device(xn_ctx* ctx, int kind, uint64_t nx, uint64_t ny, uint64
         ctx->nx = nx;
         ctx->ny = ny;
         ctx->nz = nz;
+        classify_grid(ctx);
     });
 }
 

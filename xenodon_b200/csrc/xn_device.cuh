@@ -58,6 +58,9 @@ struct FrameParams {
     // row interleave: this launch shades only the 16-row stripes s with s % il_count == il_index
     // (the same partition as il_count*... `device {}` blocks of 16 rows each, in one launch)
     uint32_t il_count, il_index;
+    // grid volumes with a substantial share of black voxels (decided at upload): the DDA skips
+    // the colour arithmetic of warp-wide empty stretches
+    uint32_t skip_empty;
 
     uint32_t* steps_out;            // stats pass only
     unsigned long long* bytes_out;  // stats pass only
@@ -77,6 +80,11 @@ __device__ __forceinline__ float min_elem(f3 v) { return gmin(v.x, gmin(v.y, v.z
 __device__ __forceinline__ float max_elem(f3 v) { return gmax(v.x, gmax(v.y, v.z)); }
 __device__ __forceinline__ float gsign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 __device__ __forceinline__ float gmod(float x, float y) { return x - y * floorf(x / y); }
+// mod(x, y) for y an exact power of two (node sizes 2^-depth): x / y equals x * (1 / y) bit for
+// bit because scaling by a power of two is exact, so the IEEE division (a reciprocal on the
+// quarter-rate pipe plus fix-up steps) becomes one multiply.  ry = pow2_reciprocal(y).
+__device__ __forceinline__ float pow2_reciprocal(float y) { return __int_as_float(0x7F000000 - __float_as_int(y)); }
+__device__ __forceinline__ float gmod_pow2(float x, float y, float ry) { return x - y * floorf(x * ry); }
 __device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ f3 cross3(f3 a, f3 b) {
     return F3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
@@ -142,12 +150,17 @@ __device__ __forceinline__ uint32_t pack_pixel(f3 c) {
 
 // Pixel owned by this thread: each warp shades an 8x4 pixel tile (rays of a warp stay
 // spatially coherent), a 256-thread block covers 16x16 pixels.
-constexpr int BLOCK_THREADS = 256;
-constexpr int BLOCK_W = 16, BLOCK_H = 16;
+// XN_BLOCK_WARPS_X warps side by side (8 pixels each), 4 warps stacked (4 rows each).
+#ifndef XN_BLOCK_WARPS_X
+#define XN_BLOCK_WARPS_X 2
+#endif
+constexpr int BLOCK_WARPS_X = XN_BLOCK_WARPS_X;
+constexpr int BLOCK_THREADS = 128 * BLOCK_WARPS_X;
+constexpr int BLOCK_W = 8 * BLOCK_WARPS_X, BLOCK_H = 16;
 __device__ __forceinline__ void thread_pixel(const FrameParams& p, uint32_t& ix, uint32_t& iy) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    ix = blockIdx.x * BLOCK_W + (warp & 1u) * 8u + (lane & 7u);
-    iy = (blockIdx.y * p.il_count + p.il_index) * BLOCK_H + (warp >> 1) * 4u + (lane >> 3);
+    ix = blockIdx.x * BLOCK_W + (warp % BLOCK_WARPS_X) * 8u + (lane & 7u);
+    iy = (blockIdx.y * p.il_count + p.il_index) * BLOCK_H + (warp / BLOCK_WARPS_X) * 4u + (lane >> 3);
 }
 
 } // namespace xn

@@ -31,6 +31,10 @@
 #ifndef XN_SVO_MIN_BLOCKS
 #define XN_SVO_MIN_BLOCKS 1
 #endif
+// DDA: skip the colour arithmetic of a trip whose texels are black across the whole warp
+#ifndef XN_DDA_SKIP_EMPTY
+#define XN_DDA_SKIP_EMPTY 1
+#endif
 // DDA: march long in-grid stretches as unchecked segments (no per-step bounds test / position)
 #ifndef XN_DDA_SEGMENTS
 #define XN_DDA_SEGMENTS 1
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
         float sdz = (sg.z * ((floorf(ro.z) - ro.z) + 0.5f) + 0.5f) * tdz;
 
         GridCursor<BIG> cur(p, px, py, pz, sx, sy, sz);
+        const bool skip_empty = XN_DDA_SKIP_EMPTY && p.skip_empty != 0u; // volume has black background
 
         // texelFetch; outside the grid -> 0 (border)
         bool inr = (uint32_t)px < p.nx && (uint32_t)py < p.ny && (uint32_t)pz < p.nz;
@@ -261,10 +266,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
         XN_DDA_STEP(N##d1) N##1 = cur.load();                                     \
         XN_DDA_STEP(N##d2) N##2 = cur.load();                                     \
         XN_DDA_STEP(N##d3) N##3 = cur.load();                                     \
-        acc.add(P##0, P##d1);                                                    \
-        acc.add(P##1, P##d2);                                                    \
-        acc.add(P##2, P##d3);                                                    \
-        acc.add(P##3, d0);                                                       \
+        /* empty space: when the four pending texels are black in every lane of the warp  */ \
+        /* the twelve conversions and twelve multiply-adds are skipped (adding 0 is exact) */ \
+        if (!skip_empty ||                                                       \
+            __any_sync(__activemask(), ((P##0 | P##1 | P##2 | P##3) & 0x00FFFFFFu) != 0u)) {   \
+            acc.add(P##0, P##d1);                                                \
+            acc.add(P##1, P##d2);                                                \
+            acc.add(P##2, P##d3);                                                \
+            acc.add(P##3, d0);                                                   \
+        }                                                                        \
     }
                         if (t < t_lim4) {
                             // set a starts as "nothing pending" except the current voxel's texel
@@ -514,9 +524,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
         }
 
         const float s2 = side * 2.0f;
-        pos.x -= gmod(pos.x, s2);
-        pos.y -= gmod(pos.y, s2);
-        pos.z -= gmod(pos.z, s2);
+        const float rs2 = pow2_reciprocal(s2);
+        pos.x -= gmod_pow2(pos.x, s2, rs2);
+        pos.y -= gmod_pow2(pos.y, s2, rs2);
+        pos.z -= gmod_pow2(pos.z, s2, rs2);
         ++child_idx;
         if (child_idx & 4u) pos.x += side;
         if (child_idx & 2u) pos.y += side;
@@ -719,9 +730,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_rope_ker
             // find_relative, svo_rope.comp:29-48
             pos = F3(ro.x + u_max * rd.x, ro.y + u_max * rd.y, ro.z + u_max * rd.z);
             side = __int_as_float((127 - (int)meta_depth(meta)) << 23); // exp2(-depth)
-            offset.x = offset.x - gmod(offset.x, side);
-            offset.y = offset.y - gmod(offset.y, side);
-            offset.z = offset.z - gmod(offset.z, side);
+            const float rside = pow2_reciprocal(side);
+            offset.x = offset.x - gmod_pow2(offset.x, side, rside);
+            offset.y = offset.y - gmod_pow2(offset.y, side, rside);
+            offset.z = offset.z - gmod_pow2(offset.z, side, rside);
             descend(p.nodes, pos, node, meta, offset, side, st);
         }
     }

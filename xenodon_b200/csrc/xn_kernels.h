@@ -9,6 +9,8 @@ cudaError_t configure_kernels();
 cudaError_t launch_traversal(int traversal, const FrameParams& p, bool stats, bool strict, cudaStream_t stream);
 cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth, cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t stream);
+cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride, unsigned long long* out,
+                               cudaStream_t stream);
 cudaError_t launch_stats_totals(const uint32_t* steps, const unsigned long long* bytes, uint64_t n,
                                 unsigned long long* totals, cudaStream_t stream);
 } // namespace xn

@@ -60,6 +60,31 @@ cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t str
     return cudaGetLastError();
 }
 
+// share of black (r = g = b = 0) voxels, from every `stride`-th voxel
+__global__ void count_black_kernel(const uint32_t* __restrict__ grid, uint64_t n, uint64_t stride,
+                                   unsigned long long* __restrict__ out) {
+    unsigned long long black = 0, seen = 0;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * stride; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x * stride) {
+        black += (grid[i] & 0x00FFFFFFu) == 0u;
+        ++seen;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        black += __shfl_xor_sync(0xFFFFFFFFu, black, o);
+        seen += __shfl_xor_sync(0xFFFFFFFFu, seen, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], black);
+        atomicAdd(&out[1], seen);
+    }
+}
+
+cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride, unsigned long long* out,
+                               cudaStream_t stream) {
+    count_black_kernel<<<148 * 8, 256, 0, stream>>>(grid, n, stride, out);
+    return cudaGetLastError();
+}
+
 // sum reduction of the stats arrays (totals for the roofline accounting)
 __global__ void stats_totals_kernel(const uint32_t* __restrict__ steps, const unsigned long long* __restrict__ bytes,
                                     uint64_t n, unsigned long long* __restrict__ totals) {

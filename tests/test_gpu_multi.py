@@ -59,3 +59,41 @@ def test_interleaved_contexts_compose_the_full_frame(xb, xo):
     ctxs[0].frame_buffer_close(ptr)
     for c in ctxs:
         c.close()
+
+
+def test_pipelined_frame_output_and_async_frame_read(xb, xo):
+    """xn_render_download_async (double-buffered targets + copy stream) and
+    xn_frame_buffer_read_async deliver the same pixels as the blocking calls."""
+    g = blobby_grid(np.random.default_rng(79), 32, 32, 32)
+    W, H = 160, 96
+    ctx = xb.Context(0)
+    ctx.set_precision(True)
+    ctx.upload_grid(xb.Grid(g))
+    ctx.set_target((0, 0, W, H))
+    ctx.set_params((1, 1, 1), None, 2.0)
+    cams = [CAMERAS["orbit"], CAMERAS["single"], CAMERAS["inside"], CAMERAS["axis_neg"], CAMERAS["orbit"]]
+    frames = [xb.PinnedFrame(W, H) for _ in cams]
+    for cam, fr in zip(cams, frames):  # five frames in flight through two alternating targets
+        ctx.render_download_async("dda", cam, fr)
+    ms = ctx.sync()
+    assert ms > 0 and ctx.launch_count() == len(cams)
+    for cam, fr in zip(cams, frames):
+        ref = xo.render("dda", grid=g, camera=cam, output=(0, 0, W, H), emission=2.0, want_stats=False)[0]
+        assert np.array_equal(fr.array, ref)
+    # async read of a shared frame buffer
+    ptr, _ = ctx.frame_buffer_create(W, H)
+    ctx.set_target_buffer(ptr, W)
+    ctx.mark(0)
+    ctx.render("dda", cams[0])
+    ctx.mark(1)
+    ctx.frame_buffer_read_async(ptr, W, H, frames[1])
+    ctx.copy_sync()
+    assert ctx.mark_elapsed() > 0
+    assert np.array_equal(frames[1].array, frames[0].array)
+    with pytest.raises(xb.XenodonError, match="external buffer"):
+        ctx.render_download_async("dda", cams[0], frames[2])
+    ctx.set_target_buffer(None, 0)
+    ctx.frame_buffer_close(ptr)
+    for fr in frames:
+        fr.free()
+    ctx.close()

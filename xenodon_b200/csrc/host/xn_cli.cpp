@@ -7,6 +7,10 @@
 // Presentation back ends (--xorg, --direct) are not part of this path and report an error.
 #include <charconv>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -49,6 +53,8 @@ struct Logger {
         localtime_r(&t, &tmv);
         std::strftime(stamp, sizeof stamp, "%H:%M:%S", &tmv);
         const std::string line = std::string("[") + stamp + "] " + msg + "\n";
+        static std::mutex mu; // the frame writer logs from its own thread
+        std::lock_guard<std::mutex> lock(mu);
         if (console) {
             std::fputs(line.c_str(), stdout);
             std::fflush(stdout);
@@ -421,6 +427,60 @@ const ShaderOption& select_shader(const RenderOptions& o, FileType type) {
     throw CliError("Failed to parse model file type");
 }
 
+// background PNG writer with a bounded queue
+class FrameWriter {
+    struct Job {
+        std::string path;
+        std::vector<uint32_t> pixels;
+        uint32_t w, h;
+    };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> queue;
+    bool done = false;
+    std::thread worker;
+
+    void run() {
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return done || !queue.empty(); });
+                if (queue.empty()) return;
+                job = std::move(queue.front());
+            }
+            LOGGER.log("Compressing...");
+            if (xn_png_write(job.path.c_str(), job.pixels.data(), job.w, job.h) != XN_OK)
+                LOGGER.log(std::string("Error saving output: ") + xn_last_error());
+            else
+                LOGGER.log("Saved output to '" + job.path + "'");
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                queue.pop_front();
+            }
+            cv.notify_all();
+        }
+    }
+
+public:
+    void submit(const std::string& path, const std::vector<uint32_t>& pixels, uint32_t w, uint32_t h) {
+        if (!worker.joinable()) worker = std::thread([this] { run(); });
+        std::unique_lock<std::mutex> lock(mu);
+        cv.wait(lock, [&] { return queue.size() < 2; });
+        queue.push_back(Job{path, pixels, w, h});
+        cv.notify_all();
+    }
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            done = true;
+        }
+        cv.notify_all();
+        if (worker.joinable()) worker.join();
+    }
+    ~FrameWriter() { finish(); }
+};
+
 struct Device {
     xn_ctx* ctx = nullptr;
     xn_rect region{};
@@ -498,6 +558,10 @@ void main_loop(const RenderOptions& o, Devices& devs, const std::string& out_pat
 
     std::vector<xn_ctx*> ctxs;
     for (auto& d : devs.v) ctxs.push_back(d.ctx);
+    // Saved frames are compressed and written by a worker thread (two frames may be in flight),
+    // so rendering frame i+1 overlaps the PNG encoding of frame i; the reference encodes
+    // synchronously on its only thread (HeadlessDisplay.cpp:78-91).
+    FrameWriter writer;
     std::vector<uint32_t> frame_pixels;
     if (!out_pattern.empty()) frame_pixels.resize((size_t)display.w * display.h);
 
@@ -531,11 +595,7 @@ void main_loop(const RenderOptions& o, Devices& devs, const std::string& out_pat
             LOGGER.log("Saving frame " + std::to_string(saved_frame) + "...");
             xn_rect enc;
             check(xn_frame_gather(ctxs.data(), (int)ctxs.size(), frame_pixels.data(), &enc));
-            LOGGER.log("Compressing...");
-            if (xn_png_write(path.c_str(), frame_pixels.data(), enc.w, enc.h) != XN_OK)
-                LOGGER.log(std::string("Error saving output: ") + xn_last_error());
-            else
-                LOGGER.log("Saved output to '" + path + "'");
+            writer.submit(path, frame_pixels, enc.w, enc.h);
         }
         ++saved_frame;
         all_stats.push_back(st);
@@ -553,6 +613,7 @@ void main_loop(const RenderOptions& o, Devices& devs, const std::string& out_pat
             start = now;
         }
     }
+    writer.finish(); // all frames are on disk before the totals are reported
     const std::chrono::duration<double> total = clock::now() - run_start;
 
     uint64_t rays = 0;

@@ -148,19 +148,24 @@ __device__ __forceinline__ uint32_t pack_pixel(f3 c) {
     return pack_unorm8(c.x) | (pack_unorm8(c.y) << 8) | (pack_unorm8(c.z) << 16) | 0xFF000000u;
 }
 
-// Pixel owned by this thread: each warp shades an 8x4 pixel tile (rays of a warp stay
-// spatially coherent), a 256-thread block covers 16x16 pixels.
-// XN_BLOCK_WARPS_X warps side by side (8 pixels each), 4 warps stacked (4 rows each).
+// Pixel owned by this thread: each warp shades a TILE_W x TILE_H pixel tile (32 pixels; rays
+// of a warp stay spatially coherent); a block is BLOCK_WARPS_X tiles wide and 16 rows tall (the
+// stripe height of xn_set_interleave).  Tunables: XN_TILE_W in {4, 8, 16, 32}, XN_BLOCK_WARPS_X.
+#ifndef XN_TILE_W
+#define XN_TILE_W 8
+#endif
 #ifndef XN_BLOCK_WARPS_X
 #define XN_BLOCK_WARPS_X 2
 #endif
-constexpr int BLOCK_WARPS_X = XN_BLOCK_WARPS_X;
-constexpr int BLOCK_THREADS = 128 * BLOCK_WARPS_X;
-constexpr int BLOCK_W = 8 * BLOCK_WARPS_X, BLOCK_H = 16;
+constexpr int TILE_W = XN_TILE_W, TILE_H = 32 / TILE_W;
+constexpr int BLOCK_WARPS_X = XN_BLOCK_WARPS_X, BLOCK_WARPS_Y = 16 / TILE_H;
+constexpr int BLOCK_THREADS = 32 * BLOCK_WARPS_X * BLOCK_WARPS_Y;
+constexpr int BLOCK_W = TILE_W * BLOCK_WARPS_X, BLOCK_H = 16;
+static_assert(TILE_W * TILE_H == 32 && BLOCK_WARPS_Y * TILE_H == 16, "tile must hold one warp");
 __device__ __forceinline__ void thread_pixel(const FrameParams& p, uint32_t& ix, uint32_t& iy) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    ix = blockIdx.x * BLOCK_W + (warp % BLOCK_WARPS_X) * 8u + (lane & 7u);
-    iy = (blockIdx.y * p.il_count + p.il_index) * BLOCK_H + (warp / BLOCK_WARPS_X) * 4u + (lane >> 3);
+    ix = blockIdx.x * BLOCK_W + (warp % BLOCK_WARPS_X) * TILE_W + (lane % TILE_W);
+    iy = (blockIdx.y * p.il_count + p.il_index) * BLOCK_H + (warp / BLOCK_WARPS_X) * TILE_H + (lane / TILE_W);
 }
 
 } // namespace xn

@@ -268,6 +268,9 @@ def main():
     if rank == 0:
         log(f"[bench] setup {time.perf_counter() - t_setup:.1f} s; frame {W}x{H}, traversal {traversal}, N={n_gpus}")
 
+    grid_layout = {xb.LAYOUT_LINEAR: "x-major linear", xb.LAYOUT_BRICKED: "8x8x8 bricks, Morton inside",
+                   xb.LAYOUT_TEXTURE: "3-D CUDA array (block-linear), texture units"}.get(
+        ctx.grid_layout()[0], "none")
     display = (0, 0, W, H)
     ctx.set_params((1, 1, 1), (nx, ny, nz) if traversal == "dda" else (tree_side,) * 3, EMISSION)
 
@@ -441,6 +444,7 @@ def main():
         "config": {
             "workload": f"{args.workload}: {wl['desc']}", "traversal": traversal, "frame": f"{W}x{H}",
             "volume": f"{kind_name} {nx}x{ny}x{nz} seed {SEED}", "camera": wl["camera"], "emission": EMISSION,
+            "grid_layout": grid_layout if traversal == "dda" else None,
             "partition": ("single region" if n_gpus == 1 else
                           f"16-row stripes round-robin over {n_gpus} GPUs, peer stores into rank 0's frame (CUDA IPC/NVLink)"
                           if args.gather == "ipc" else f"{n_gpus} horizontal bands, NCCL send/recv gather to rank 0"),

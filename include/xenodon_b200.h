@@ -121,6 +121,24 @@ XN_API int xn_synth_grid_host(int kind, uint64_t nx, uint64_t ny, uint64_t nz, u
 /* copy the bound grid back to the host (nx*ny*nz*4 bytes) */
 XN_API int xn_download_grid(xn_ctx* ctx, uint8_t* rgba_out, uint64_t cap_bytes);
 
+/* Residency layout of the grid in HBM.  The reference hands its grid to the driver as an
+ * "optimal tiling" 3-D image (src/render/DdaRaytraceAlgorithm.cpp:16-34); here the order is
+ * explicit: x-major linear, or 8x8x8 bricks with Morton order inside (one 32-byte sector = a
+ * 2x2x2 voxel cube), which keeps a warp's texels in few sectors whatever the ray direction.
+ * AUTO (default) bricks large volumes only.  The mode applies to the grid resident now and to
+ * later uploads; images are identical in every layout.  xn_grid_layout reports what is resident
+ * (XN_GRID_LAYOUT_AUTO = no grid) and the bytes it occupies. */
+enum { XN_GRID_LAYOUT_AUTO = 0, XN_GRID_LAYOUT_LINEAR = 1, XN_GRID_LAYOUT_BRICKED = 2, XN_GRID_LAYOUT_TEXTURE = 3 };
+XN_API int xn_set_grid_layout(xn_ctx* ctx, int mode);
+XN_API int xn_grid_layout(const xn_ctx* ctx, int* layout_out, uint64_t* resident_bytes_out);
+/* The bricked index function itself (host arithmetic, no device needed): desc_out = index-bit
+ * masks of x, y, z, bit position of each axis' brick field, the top axis, total voxel slots
+ * (padding included).  top = -1 lets the library choose, as uploads do.  xn_brick_indices maps
+ * n (x, y, z) triples to slot indices; -1 and n_axis wrap inside the axis' own bits. */
+XN_API int xn_brick_layout(uint64_t nx, uint64_t ny, uint64_t nz, int top, uint64_t desc_out[8]);
+XN_API int xn_brick_indices(uint64_t nx, uint64_t ny, uint64_t nz, int top, const int32_t* xyz, uint64_t n,
+                            uint64_t* index_out);
+
 /* ---- per-output uniforms: Renderer::upload_uniform_buffers, src/render/Renderer.cpp:236-268 ----
  * output  = this device's region (HeadlessConfig device{offset,extent});
  * display = union of all regions (RenderContext::calculate_display_rect,

@@ -203,7 +203,9 @@ def test_dda_64bit_index_kernel_matches_oracle(xb):
         "g = random_grid(np.random.default_rng(64), 48, 31, 40)\n"
         "for cam in ('orbit', 'inside', 'axis_neg'):\n"
         "    for strict in (True, False):\n"
-        "        ctx = xb.Context(0); ctx.set_precision(strict); ctx.upload_grid(xb.Grid(g))\n"
+        "      for layout in (xb.LAYOUT_LINEAR, xb.LAYOUT_BRICKED, xb.LAYOUT_TEXTURE):\n"
+        "        ctx = xb.Context(0); ctx.set_precision(strict); ctx.set_grid_layout(layout); ctx.upload_grid(xb.Grid(g))\n"
+        "        assert ctx.grid_layout()[0] == layout\n"
         "        ctx.set_target((0, 0, 160, 90)); ctx.set_params((1, 1, 1), None, 2.0)\n"
         "        ctx.render('dda', CAMERAS[cam]); ctx.sync(); img = ctx.download()\n"
         "        steps = ctx.stats_pass('dda', CAMERAS[cam])[0]; ctx.close()\n"
@@ -216,3 +218,74 @@ def test_dda_64bit_index_kernel_matches_oracle(xb):
     env = dict(os.environ, XN_FORCE_IDX64="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "IDX64 OK" in r.stdout, r.stderr[-2000:]
+
+
+BRICK_DIMS = [(16, 16, 16), (33, 20, 9), (64, 45, 64), (5, 70, 3), (40, 8, 129)]
+
+
+@pytest.mark.parametrize("layout", ["bricked", "texture"])
+@pytest.mark.parametrize("cam", ["orbit", "inside", "oblique", "axis_neg"])
+@pytest.mark.parametrize("dims", BRICK_DIMS)
+def test_dda_resident_layouts_match_oracle(xb, xo, cam, dims, layout):
+    """The bricked residency (8x8x8 bricks, Morton inside; xn_brick.h) and the texture residency
+    (3-D CUDA array read through the texture units, border = 0) change only where a voxel lives in
+    HBM and who computes its address: images, per-ray step counts and the grid read back are those
+    of the linear layout."""
+    mode = {"bricked": xb.LAYOUT_BRICKED, "texture": xb.LAYOUT_TEXTURE}[layout]
+    rng = np.random.default_rng(hash((cam, dims)) & 0xFFFF)
+    g = random_grid(rng, *dims)
+    kw = dict(camera=CAMERAS[cam], output=(0, 0, 160, 90), emission=2.0)
+    ref, rsteps, rbytes = xo.render("dda", grid=g, **kw)
+    for strict in (True, False):
+        ctx = xb.Context(0)
+        try:
+            ctx.set_precision(strict)
+            ctx.set_grid_layout(mode)
+            ctx.upload_grid(xb.Grid(g))
+            have, nbytes = ctx.grid_layout()
+            assert have == mode and nbytes >= g.nbytes and (layout == "texture" or nbytes % 2048 == 0)
+            ctx.set_target((0, 0, 160, 90))
+            ctx.set_params((1, 1, 1), None, 2.0)
+            ctx.render("dda", CAMERAS[cam])
+            ctx.sync()
+            img = ctx.download()
+            steps, nbytes_ray, _ = ctx.stats_pass("dda", CAMERAS[cam])
+            back = ctx.download_grid().data
+            assert ctx.grid_layout()[0] == mode  # the read-back leaves the layout resident
+            # switching the layout of a resident grid re-lays it out in place
+            ctx.set_grid_layout(xb.LAYOUT_LINEAR)
+            assert ctx.grid_layout() == (xb.LAYOUT_LINEAR, g.nbytes)
+            ctx.render("dda", CAMERAS[cam])
+            ctx.sync()
+            img_linear = ctx.download()
+        finally:
+            ctx.close()
+        assert np.array_equal(back, g)
+        assert np.array_equal(steps, rsteps) and np.array_equal(nbytes_ray, rbytes)
+        if strict or layout == "bricked":
+            assert np.array_equal(img, img_linear)
+        else:  # fast mode: the texture unit's c / 255 floats vs bytes scaled once per ray
+            assert image_diff(img, img_linear)[0] <= 1
+        if strict:
+            assert np.array_equal(img, ref)
+        else:
+            assert image_diff(img, ref)[0] <= 1
+
+
+def test_dda_bricked_gpu_convert_and_auto_policy(xb):
+    """GPU convert reads the grid through the linear view whatever is resident; AUTO keeps small
+    grids linear and XN_BRICK_MIN_VOXELS moves the threshold."""
+    rng = np.random.default_rng(3)
+    g = blobby_grid(rng, 40, 29, 33)
+    host_tree, _ = xb.build_octree(xb.Grid(g), chan_diff=0, type=xb.TYPE_SPARSE)
+    ctx = xb.Context(0)
+    try:
+        ctx.upload_grid(xb.Grid(g))
+        assert ctx.grid_layout()[0] == xb.LAYOUT_LINEAR  # AUTO: far below the threshold
+        ctx.set_grid_layout(xb.LAYOUT_BRICKED)
+        tree, _, count, side = ctx.convert_resident_grid(0, xb.TYPE_SPARSE, bind=False, want_nodes=True)
+        assert ctx.grid_layout()[0] == xb.LAYOUT_BRICKED
+        assert count == len(host_tree.nodes) and side == host_tree.side
+        assert tree.nodes.tobytes() == host_tree.nodes.tobytes()
+    finally:
+        ctx.close()

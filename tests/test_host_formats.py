@@ -264,3 +264,44 @@ def test_synthetic_volumes_have_the_named_shapes(xb):
     assert 0.8 < floor < 0.97 and (t[..., 3] == 255).all()
     assert np.array_equal(t, xb.Grid.synthetic(xb.SYNTH_TNG, 64, 64, 64).data)  # deterministic
     assert not np.array_equal(t, xb.Grid.synthetic(xb.SYNTH_TNG, 64, 64, 64, seed=7).data)
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 16), (33, 20, 9), (5, 70, 3), (40, 8, 129), (512, 361, 512)])
+def test_bricked_layout_index_function(xb, dims):
+    """csrc/xn_brick.h: the slot index is a bijection onto [0, total), a 32-byte sector holds a
+    2x2x2 voxel cube, the axis padded worst sits on top (no power-of-two padding there), and a DDA
+    step is (d + K) & mask on the axis' own bits -- including the wrap at -1 and n."""
+    nx, ny, nz = dims
+    L = xb.brick_layout(nx, ny, nz)
+    mx, my, mz = L["mask"]
+    assert mx & my == 0 and mx & mz == 0 and my & mz == 0
+    nb = [(n + 7) // 8 for n in dims]
+    pad = [(1 << max(0, (b - 1).bit_length())) / b for b in nb]
+    assert pad[L["top"]] == max(pad)
+    lower = [a for a in range(3) if a != L["top"]]
+    total = 512 * nb[L["top"]]
+    for a in lower:
+        total *= 1 << max(0, (nb[a] - 1).bit_length())
+    assert L["total"] == total
+    if nx * ny * nz <= 1 << 18:
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        xyz = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    else:
+        xyz = np.random.default_rng(1).integers(0, dims, (200000, 3))
+        xyz = np.unique(xyz, axis=0)
+    idx = xb.brick_indices(nx, ny, nz, xyz)
+    assert idx.max() < L["total"] and len(np.unique(idx)) == len(idx)
+    # one sector (8 consecutive slots) = one 2x2x2 cube; one 2 KiB brick = one 8x8x8 cube
+    assert np.array_equal(idx >> np.uint64(3) == (idx[0] >> np.uint64(3)), (xyz >> 1 == xyz[0] >> 1).all(axis=1))
+    assert np.array_equal(idx >> np.uint64(9) == (idx[0] >> np.uint64(9)), (xyz >> 3 == xyz[0] >> 3).all(axis=1))
+    # stepping: x from -1 to nx (the kernel's cursor passes through both while out of range)
+    for axis, n in enumerate(dims):
+        mask = L["mask"][axis] & 0xFFFFFFFFFFFFFFFF
+        pts = np.zeros((n + 2, 3), np.int32)
+        pts[:, axis] = np.arange(-1, n + 1)
+        d = [int(v) & mask for v in xb.brick_indices(nx, ny, nz, pts)]
+        for i in range(len(d) - 1):
+            assert (d[i] - mask) & 0xFFFFFFFFFFFFFFFF & mask == d[i + 1]      # +1: K = -mask
+            assert (d[i + 1] - 1) & 0xFFFFFFFFFFFFFFFF & mask == d[i]          # -1: K = -1
+    # a forced top axis (the 64-bit cursor wants z on top) is honoured
+    assert xb.brick_layout(nx, ny, nz, 2)["top"] == 2

@@ -25,6 +25,7 @@ TRAVERSALS = {"dda": DDA, "svo-naive": SVO_NAIVE, "esvo": ESVO, "svo-df": SVO_DF
 TYPE_SPARSE, TYPE_DAG, TYPE_ROPE = range(3)
 HEUR_CHAN_DIFF, HEUR_STD_DEV = range(2)
 SYNTH_BUNNY, SYNTH_TNG = 0, 1
+LAYOUT_AUTO, LAYOUT_LINEAR, LAYOUT_BRICKED, LAYOUT_TEXTURE = range(4)
 
 NODE_DTYPE = np.dtype([("children", "<u4", (8,)), ("color", "<u4"), ("is_leaf_depth", "<u4")])
 assert NODE_DTYPE.itemsize == 40
@@ -83,6 +84,10 @@ _PROTOTYPES = {
     "xn_synth_grid_device": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]),
     "xn_synth_grid_host": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "xn_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "xn_set_grid_layout": (C.c_int, [C.c_void_p, C.c_int]),
+    "xn_grid_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
+    "xn_brick_layout": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    "xn_brick_indices": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]),
     "xn_set_target": (C.c_int, [C.c_void_p, C.POINTER(Rect), C.POINTER(Rect)]),
     "xn_set_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_uint32 * 3), C.c_float]),
     "xn_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
@@ -220,6 +225,20 @@ class Octree:
         _check(lib().xn_svo_write(os.fsencode(path), self.nodes.ctypes.data, len(self.nodes), self.side))
 
 
+def brick_layout(nx: int, ny: int, nz: int, top: int = -1) -> dict:
+    """Bricked residency layout of an nx*ny*nz grid (csrc/xn_brick.h)."""
+    d = (C.c_uint64 * 8)()
+    _check(lib().xn_brick_layout(nx, ny, nz, top, d))
+    return {"mask": tuple(d[0:3]), "hs": tuple(d[3:6]), "top": int(d[6]), "total": int(d[7])}
+
+
+def brick_indices(nx: int, ny: int, nz: int, xyz, top: int = -1) -> np.ndarray:
+    xyz = np.ascontiguousarray(xyz, dtype=np.int32).reshape(-1, 3)
+    out = np.empty(len(xyz), dtype=np.uint64)
+    _check(lib().xn_brick_indices(nx, ny, nz, top, xyz.ctypes.data, len(xyz), out.ctypes.data))
+    return out
+
+
 def build_octree(grid: Grid, *, chan_diff=None, std_dev=None, type: int = TYPE_SPARSE):
     """`xenodon convert` (reference OctreeConstruction.h:226-237).  Returns (Octree, stats dict)."""
     if chan_diff is not None and std_dev is not None:
@@ -311,6 +330,16 @@ class Context:
     def synth_grid(self, kind: int, nx: int, ny: int, nz: int, seed: int = 1729):
         _check(lib().xn_synth_grid_device(self._h, kind, nx, ny, nz, seed))
         self.model_dim = (nx, ny, nz)
+
+    def set_grid_layout(self, mode: int):
+        """Residency layout of the grid in HBM (LAYOUT_AUTO / LAYOUT_LINEAR / LAYOUT_BRICKED)."""
+        _check(lib().xn_set_grid_layout(self._h, mode))
+
+    def grid_layout(self):
+        """(layout resident now, bytes it occupies)."""
+        layout, nbytes = C.c_int(), C.c_uint64()
+        _check(lib().xn_grid_layout(self._h, C.byref(layout), C.byref(nbytes)))
+        return layout.value, nbytes.value
 
     def download_grid(self) -> Grid:
         nx, ny, nz = self.model_dim

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -85,7 +86,12 @@ struct xn_ctx {
     double last_ms = 0;
 
     // volume
-    uint32_t* grid = nullptr;
+    uint32_t* grid = nullptr;   // x-major linear copy (may be absent while the bricked copy is resident)
+    uint32_t* bricks = nullptr; // bricked copy (xn_brick.h), what the DDA reads when present
+    xn::BrickLayout brick_layout{};
+    cudaArray_t tex_array = nullptr; // texture residency: 3-D array + two views of it
+    cudaTextureObject_t tex_unorm = 0, tex_raw = 0;
+    int layout_mode = XN_GRID_LAYOUT_AUTO;
     uint64_t nx = 0, ny = 0, nz = 0;
     xn::DNode* nodes = nullptr;
     uint64_t node_count = 0, side = 0;
@@ -111,11 +117,21 @@ struct xn_ctx {
 
     std::vector<void*> ipc_opened;
 
+    void free_texture() {
+        if (tex_unorm) cudaDestroyTextureObject(tex_unorm);
+        if (tex_raw) cudaDestroyTextureObject(tex_raw);
+        if (tex_array) cudaFreeArray(tex_array);
+        tex_unorm = tex_raw = 0;
+        tex_array = nullptr;
+    }
     void free_grid() {
         if (grid) cudaFree(grid);
-        grid = nullptr;
+        if (bricks) cudaFree(bricks);
+        free_texture();
+        grid = bricks = nullptr;
         nx = ny = nz = 0;
     }
+    bool have_grid() const { return grid || bricks || tex_array; }
     void free_nodes() {
         if (nodes) cudaFree(nodes);
         nodes = nullptr;
@@ -136,7 +152,7 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     if (!ctx->have_params) throw xn::Error(XN_ERR_INVALID, "xn_set_params has not been called");
     if (!fwd || !up || !tr) throw xn::Error(XN_ERR_INVALID, "null camera vector");
     if (traversal == XN_DDA) {
-        if (!ctx->grid)
+        if (!ctx->have_grid())
             throw xn::Error(XN_ERR_INVALID, "Shader 'dda' is incompatible with model type 'svo' (requires 'tiff')");
     } else if (!ctx->nodes) {
         throw xn::Error(XN_ERR_INVALID, std::string("Shader '") + TRAVERSAL_NAMES[traversal] +
@@ -167,6 +183,19 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
         p.target_stride = ctx->output.w;
     }
     p.grid = ctx->grid;
+    if (ctx->bricks) {
+        const xn::BrickLayout& L = ctx->brick_layout;
+        p.grid = ctx->bricks;
+        for (int i = 0; i < 3; ++i) {
+            p.bk_mask[i] = (uint32_t)L.mask[i];
+            p.bk_hs[i] = L.hs[i];
+        }
+        p.bk_top = L.top;
+        p.bk_mask_z64 = L.mask[2];
+        p.bk_slots = L.total;
+    }
+    p.tex_unorm = ctx->tex_unorm;
+    p.tex_raw = ctx->tex_raw;
     p.nx = (uint32_t)ctx->nx;
     p.ny = (uint32_t)ctx->ny;
     p.nz = (uint32_t)ctx->nz;
@@ -191,6 +220,117 @@ void classify_grid(xn_ctx* ctx) {
     cudaFree(d);
     if (e != cudaSuccess) throw CudaError{e, "classify_grid"};
     ctx->grid_has_black_background = h[1] > 0 && h[0] * 4 >= h[1];
+}
+
+// ---- resident layout of the grid (xn_brick.h) ----
+
+bool env_force_idx64() {
+    const char* e = std::getenv("XN_FORCE_IDX64");
+    return e && e[0] == '1';
+}
+
+// layout the bricked copy of this grid would have; false if the DDA has no cursor for it
+bool plan_bricks(const xn_ctx* ctx, xn::BrickLayout& L) {
+    L = xn::make_brick_layout(ctx->nx, ctx->ny, ctx->nz, env_force_idx64() ? 2 : -1);
+    if (L.total <= (1ull << 32) && !env_force_idx64()) return true;
+    if (L.top != 2) L = xn::make_brick_layout(ctx->nx, ctx->ny, ctx->nz, 2);
+    return L.hs[2] <= 32;
+}
+
+// which residency the layout mode asks for.  AUTO: volumes far larger than L2 go to the texture
+// residency, where a warp's texels share sectors whatever the ray direction and the texture unit
+// does the addressing (measured: profiles/README.md); small grids stay x-major linear.
+int wanted_layout(const xn_ctx* ctx, xn::BrickLayout& L) {
+    const uint64_t voxels = ctx->nx * ctx->ny * ctx->nz;
+    const bool tex_ok = ctx->nx <= 16384 && ctx->ny <= 16384 && ctx->nz <= 16384;
+    switch (ctx->layout_mode) {
+        case XN_GRID_LAYOUT_LINEAR: return XN_GRID_LAYOUT_LINEAR;
+        case XN_GRID_LAYOUT_BRICKED: return plan_bricks(ctx, L) ? XN_GRID_LAYOUT_BRICKED : XN_GRID_LAYOUT_LINEAR;
+        case XN_GRID_LAYOUT_TEXTURE: return tex_ok ? XN_GRID_LAYOUT_TEXTURE : XN_GRID_LAYOUT_LINEAR;
+        default: break;
+    }
+    uint64_t min_voxels = 1ull << 29;
+    if (const char* e = std::getenv("XN_TEXTURE_MIN_VOXELS")) min_voxels = std::strtoull(e, nullptr, 10);
+    return tex_ok && voxels >= min_voxels ? XN_GRID_LAYOUT_TEXTURE : XN_GRID_LAYOUT_LINEAR;
+}
+
+cudaMemcpy3DParms array_copy_parms(xn_ctx* ctx, bool to_array) {
+    cudaMemcpy3DParms cp{};
+    const cudaPitchedPtr lin = make_cudaPitchedPtr(ctx->grid, ctx->nx * 4, ctx->nx, ctx->ny);
+    if (to_array) {
+        cp.srcPtr = lin;
+        cp.dstArray = ctx->tex_array;
+    } else {
+        cp.srcArray = ctx->tex_array;
+        cp.dstPtr = lin;
+    }
+    cp.extent = make_cudaExtent(ctx->nx, ctx->ny, ctx->nz);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    return cp;
+}
+
+void ensure_linear(xn_ctx* ctx) {
+    if (ctx->grid) return;
+    if (!ctx->bricks && !ctx->tex_array) return;
+    XN_CUDA(cudaMalloc(&ctx->grid, ctx->nx * ctx->ny * ctx->nz * 4));
+    if (ctx->bricks) {
+        XN_CUDA(xn::launch_unbrick_grid(ctx->bricks, ctx->grid, ctx->brick_layout, (uint32_t)ctx->nx, (uint32_t)ctx->ny,
+                                        (uint32_t)ctx->nz, ctx->stream));
+    } else {
+        const cudaMemcpy3DParms cp = array_copy_parms(ctx, false);
+        XN_CUDA(cudaMemcpy3DAsync(&cp, ctx->stream));
+    }
+    XN_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void make_texture(xn_ctx* ctx) {
+    const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    XN_CUDA(cudaMalloc3DArray(&ctx->tex_array, &fmt, make_cudaExtent(ctx->nx, ctx->ny, ctx->nz)));
+    const cudaMemcpy3DParms cp = array_copy_parms(ctx, true);
+    XN_CUDA(cudaMemcpy3DAsync(&cp, ctx->stream));
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = ctx->tex_array;
+    cudaTextureDesc td{};
+    // nearest, unnormalised coordinates, transparent-black border: the reference's sampler
+    // (src/render/DdaRaytraceAlgorithm.cpp:16-34)
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+    td.filterMode = cudaFilterModePoint;
+    td.normalizedCoords = 0;
+    td.readMode = cudaReadModeNormalizedFloat;
+    XN_CUDA(cudaCreateTextureObject(&ctx->tex_unorm, &res, &td, nullptr));
+    td.readMode = cudaReadModeElementType;
+    XN_CUDA(cudaCreateTextureObject(&ctx->tex_raw, &res, &td, nullptr));
+    XN_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// make the resident copies match the layout mode: exactly one copy stays resident
+void apply_layout(xn_ctx* ctx) {
+    if (!ctx->have_grid()) return;
+    xn::BrickLayout L;
+    const int want = wanted_layout(ctx, L);
+    const int have = ctx->tex_array ? XN_GRID_LAYOUT_TEXTURE : (ctx->bricks ? XN_GRID_LAYOUT_BRICKED : XN_GRID_LAYOUT_LINEAR);
+    if (want != have || (want != XN_GRID_LAYOUT_LINEAR && ctx->grid)) {
+        if (want != have) {
+            ensure_linear(ctx);
+            if (ctx->bricks) cudaFree(ctx->bricks);
+            ctx->bricks = nullptr;
+            ctx->free_texture();
+            if (want == XN_GRID_LAYOUT_BRICKED) {
+                XN_CUDA(cudaMalloc(&ctx->bricks, L.total * 4));
+                ctx->brick_layout = L;
+                XN_CUDA(xn::launch_brick_grid(ctx->grid, ctx->bricks, L, (uint32_t)ctx->nx, (uint32_t)ctx->ny,
+                                              (uint32_t)ctx->nz, ctx->stream));
+                XN_CUDA(cudaStreamSynchronize(ctx->stream));
+            } else if (want == XN_GRID_LAYOUT_TEXTURE) {
+                make_texture(ctx);
+            }
+        }
+        if (want != XN_GRID_LAYOUT_LINEAR) {
+            if (ctx->grid) cudaFree(ctx->grid);
+            ctx->grid = nullptr;
+        }
+    }
 }
 
 void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) {
@@ -261,6 +401,11 @@ int xn_ctx_create(int cuda_device, xn_ctx** out) {
         DeviceGuard g(cuda_device);
         auto ctx = std::make_unique<xn_ctx>();
         ctx->device = cuda_device;
+        if (const char* e = std::getenv("XN_GRID_LAYOUT")) { // default mode of new contexts (A/B runs)
+            if (std::strcmp(e, "linear") == 0) ctx->layout_mode = XN_GRID_LAYOUT_LINEAR;
+            else if (std::strcmp(e, "bricked") == 0) ctx->layout_mode = XN_GRID_LAYOUT_BRICKED;
+            else if (std::strcmp(e, "texture") == 0) ctx->layout_mode = XN_GRID_LAYOUT_TEXTURE;
+        }
         XN_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         XN_CUDA(cudaEventCreate(&ctx->ev_start));
         XN_CUDA(cudaEventCreate(&ctx->ev_stop));
@@ -330,6 +475,7 @@ int xn_upload_grid(xn_ctx* ctx, const uint8_t* rgba, uint64_t nx, uint64_t ny, u
         ctx->ny = ny;
         ctx->nz = nz;
         classify_grid(ctx);
+        apply_layout(ctx);
     });
 }
 
@@ -348,6 +494,7 @@ int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t
         ctx->ny = ny;
         ctx->nz = nz;
         classify_grid(ctx);
+        apply_layout(ctx);
     });
 }
 
@@ -387,12 +534,13 @@ int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_
                              uint64_t* side_out, xn_build_stats* stats_out) {
     return guarded([&] {
         check_ctx(ctx);
-        if (!ctx->grid) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
+        if (!ctx->have_grid()) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
         if (chan_diff < 0 || chan_diff > 255) throw xn::Error(XN_ERR_INVALID, "channel difference must be 0..255");
         if (type != 0 && type != 2)
             throw xn::Error(XN_ERR_INVALID, "the GPU builder makes sparse (0) and rope (2) trees; --dag is host-only");
         if (nodes_out) *nodes_out = nullptr;
         DeviceGuard g(ctx->device);
+        ensure_linear(ctx); // the builder reads the x-major copy
         void* d_nodes = nullptr;
         uint64_t count = 0, side = 0;
         xn::gpu_build_octree(ctx->grid, ctx->nx, ctx->ny, ctx->nz, (uint32_t)chan_diff, type == 2, ctx->stream, &d_nodes,
@@ -415,6 +563,7 @@ int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_
             throw;
         }
         cudaFree(d_nodes);
+        apply_layout(ctx);
         if (count_out) *count_out = count;
         if (side_out) *side_out = side;
     });
@@ -436,6 +585,7 @@ int xn_synth_grid_device(xn_ctx* ctx, int kind, uint64_t nx, uint64_t ny, uint64
         ctx->ny = ny;
         ctx->nz = nz;
         classify_grid(ctx);
+        apply_layout(ctx);
     });
 }
 
@@ -449,12 +599,59 @@ int xn_synth_grid_host(int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t
 int xn_download_grid(xn_ctx* ctx, uint8_t* rgba_out, uint64_t cap_bytes) {
     return guarded([&] {
         check_ctx(ctx);
-        if (!ctx->grid) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
+        if (!ctx->have_grid()) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
         const uint64_t bytes = ctx->nx * ctx->ny * ctx->nz * 4;
         if (!rgba_out || cap_bytes < bytes) throw xn::Error(XN_ERR_INVALID, "output buffer too small");
         DeviceGuard g(ctx->device);
+        ensure_linear(ctx);
         XN_CUDA(cudaMemcpyAsync(rgba_out, ctx->grid, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        apply_layout(ctx);
+    });
+}
+
+int xn_set_grid_layout(xn_ctx* ctx, int mode) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (mode < XN_GRID_LAYOUT_AUTO || mode > XN_GRID_LAYOUT_TEXTURE) throw xn::Error(XN_ERR_INVALID, "unknown grid layout");
+        DeviceGuard g(ctx->device);
+        ctx->layout_mode = mode;
+        apply_layout(ctx);
+        if (mode != XN_GRID_LAYOUT_AUTO && mode != XN_GRID_LAYOUT_LINEAR && ctx->grid)
+            throw xn::Error(XN_ERR_LIMIT, "grid shape is outside the limits of the requested layout");
+    });
+}
+
+int xn_grid_layout(const xn_ctx* ctx, int* layout_out, uint64_t* resident_bytes_out) {
+    if (!ctx || !layout_out) return fail(XN_ERR_INVALID, "null argument");
+    *layout_out = ctx->tex_array ? XN_GRID_LAYOUT_TEXTURE
+                                 : (ctx->bricks ? XN_GRID_LAYOUT_BRICKED : (ctx->grid ? XN_GRID_LAYOUT_LINEAR : XN_GRID_LAYOUT_AUTO));
+    if (resident_bytes_out)
+        *resident_bytes_out = (ctx->bricks ? ctx->brick_layout.total * 4 : 0) +
+                              ((ctx->grid ? 1 : 0) + (ctx->tex_array ? 1 : 0)) * ctx->nx * ctx->ny * ctx->nz * 4;
+    return XN_OK;
+}
+
+int xn_brick_layout(uint64_t nx, uint64_t ny, uint64_t nz, int top, uint64_t desc_out[8]) {
+    return guarded([&] {
+        if (!desc_out || nx == 0 || ny == 0 || nz == 0 || top > 2) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        const xn::BrickLayout L = xn::make_brick_layout(nx, ny, nz, top);
+        for (int a = 0; a < 3; ++a) {
+            desc_out[a] = L.mask[a];
+            desc_out[3 + a] = L.hs[a];
+        }
+        desc_out[6] = L.top;
+        desc_out[7] = L.total;
+    });
+}
+
+int xn_brick_indices(uint64_t nx, uint64_t ny, uint64_t nz, int top, const int32_t* xyz, uint64_t n, uint64_t* index_out) {
+    return guarded([&] {
+        if (!xyz || !index_out || nx == 0 || ny == 0 || nz == 0 || top > 2) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        const xn::BrickLayout L = xn::make_brick_layout(nx, ny, nz, top);
+        for (uint64_t i = 0; i < n; ++i)
+            index_out[i] = xn::brick_axis(L, 0, xyz[3 * i]) | xn::brick_axis(L, 1, xyz[3 * i + 1]) |
+                           xn::brick_axis(L, 2, xyz[3 * i + 2]);
     });
 }
 

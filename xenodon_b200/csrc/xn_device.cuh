@@ -49,8 +49,15 @@ struct FrameParams {
     uint32_t* target;      // RGBA8 pixels, may point into a peer device's frame
     uint64_t target_stride; // in pixels
 
-    const uint32_t* grid;   // RGBA8 voxels, x fastest
+    const uint32_t* grid;   // RGBA8 voxels: x fastest, or bricked (xn_brick.h) when bk_slots != 0
     uint32_t nx, ny, nz;
+    // bricked residency: index bits owned by x, y, z (low 32 bits), position of each axis'
+    // brick-index field, the axis on top, z's full 64-bit mask, number of voxel slots (0 = linear)
+    uint32_t bk_mask[3], bk_hs[3], bk_top;
+    uint64_t bk_mask_z64, bk_slots;
+    // texture residency: the grid as a 3-D CUDA array (block-linear tiling, border = 0) seen through
+    // two texture objects: channels as c / 255 floats (fast mode) and as raw bytes (strict mode)
+    unsigned long long tex_unorm, tex_raw;
     const DNode* nodes;
     uint32_t root_meta;
     uint32_t max_depth;     // deepest node depth in the tree (stack sizing)

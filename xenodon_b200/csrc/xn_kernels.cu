@@ -19,6 +19,7 @@
 //            per ray.  Differs from STRICT by at most 1/255 on a small fraction of pixels.
 #include <cstdlib>
 
+#include "xn_brick.h"
 #include "xn_device.cuh"
 #include "xn_kernels.h"
 
@@ -171,13 +172,87 @@ struct GridCursor<true> {
     }
 };
 
+// Cursor over the bricked layout (xn_brick.h): every axis keeps its own dilated coordinate, a
+// step is one add and one mask on that coordinate, the voxel index is the OR of the three.
+//   BrickCursor<false>: 32-bit index (up to 2^32 voxel slots, any axis on top).
+//   BrickCursor<true> : z on top with a 64-bit dilated coordinate; x and y stay 32-bit.
+template <bool BIG>
+struct BrickCursor;
+
+// a | b | c as ONE LOP3 (the compiler otherwise emits two two-input ORs per texel address)
+__device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xFE;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <>
+struct BrickCursor<false> {
+    const uint32_t* __restrict__ grid;
+    uint32_t dx, dy, dz, kx, ky, kz, mx, my, mz, hx, hy, hz;
+    static __device__ __forceinline__ uint32_t enc(int c, int axis, uint32_t hs, uint32_t mask) {
+        return ((brick_m3((uint32_t)c & 7u) << axis) | ((uint32_t)(c >> 3) << hs)) & mask;
+    }
+    static __device__ __forceinline__ int dec(uint32_t d, int axis, uint32_t hs) {
+        return (int)(((d >> hs) << 3) | brick_c3(d >> axis));
+    }
+    __device__ __forceinline__ BrickCursor(const FrameParams& p, int px, int py, int pz, int sx, int sy, int sz)
+        : grid(p.grid), mx(p.bk_mask[0]), my(p.bk_mask[1]), mz(p.bk_mask[2]), hx(p.bk_hs[0]), hy(p.bk_hs[1]),
+          hz(p.bk_hs[2]) {
+        dx = enc(px, 0, hx, mx);
+        dy = enc(py, 1, hy, my);
+        dz = enc(pz, 2, hz, mz);
+        kx = sx > 0 ? 0u - mx : 0xFFFFFFFFu;
+        ky = sy > 0 ? 0u - my : 0xFFFFFFFFu;
+        kz = sz > 0 ? 0u - mz : 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ void step_x() { dx = (dx + kx) & mx; }
+    __device__ __forceinline__ void step_y() { dy = (dy + ky) & my; }
+    __device__ __forceinline__ void step_z() { dz = (dz + kz) & mz; }
+    __device__ __forceinline__ uint32_t load() const { return __ldg(grid + or3(dx, dy, dz)); }
+    __device__ __forceinline__ void recover(int& px, int& py, int& pz) const {
+        px = dec(dx, 0, hx);
+        py = dec(dy, 1, hy);
+        pz = dec(dz, 2, hz);
+    }
+};
+
+template <>
+struct BrickCursor<true> {
+    const uint32_t* __restrict__ grid;
+    uint64_t dz, kz, mz;
+    uint32_t dx, dy, kx, ky, mx, my, hx, hy, hz;
+    __device__ __forceinline__ BrickCursor(const FrameParams& p, int px, int py, int pz, int sx, int sy, int sz)
+        : grid(p.grid), mz(p.bk_mask_z64), mx(p.bk_mask[0]), my(p.bk_mask[1]), hx(p.bk_hs[0]), hy(p.bk_hs[1]),
+          hz(p.bk_hs[2]) {
+        dx = BrickCursor<false>::enc(px, 0, hx, mx);
+        dy = BrickCursor<false>::enc(py, 1, hy, my);
+        dz = (((uint64_t)brick_m3((uint32_t)pz & 7u) << 2) | ((uint64_t)(int64_t)(pz >> 3) << hz)) & mz;
+        kx = sx > 0 ? 0u - mx : 0xFFFFFFFFu;
+        ky = sy > 0 ? 0u - my : 0xFFFFFFFFu;
+        kz = sz > 0 ? 0ull - mz : ~0ull;
+    }
+    __device__ __forceinline__ void step_x() { dx = (dx + kx) & mx; }
+    __device__ __forceinline__ void step_y() { dy = (dy + ky) & my; }
+    __device__ __forceinline__ void step_z() { dz = (dz + kz) & mz; }
+    __device__ __forceinline__ uint32_t load() const {
+        return __ldg(grid + (((dz >> 32) << 32) | (uint64_t)or3(dx, dy, (uint32_t)dz)));
+    }
+    __device__ __forceinline__ void recover(int& px, int& py, int& pz) const {
+        px = BrickCursor<false>::dec(dx, 0, hx);
+        py = BrickCursor<false>::dec(dy, 1, hy);
+        pz = (int)(((dz >> hz) << 3) | brick_c3(dz >> 2));
+    }
+};
+
 // ---------------------------------------------------------------------------------
 // DDA (resources/dda.comp:13-73)
-// BIG selects the addressing of grids of 2^31 voxels and more (GridCursor).
+// CURSOR selects the resident layout and index width: GridCursor<false/true> = x-major linear
+// (32-bit index / grids of 2^31 voxels and more), BrickCursor<false/true> = bricked (xn_brick.h).
 // Texels are requested ahead of their accumulation (their addresses never depend on loaded
 // data), so every warp overlaps its own load latency with arithmetic.
 // ---------------------------------------------------------------------------------
-template <bool STATS, bool STRICT, bool BIG>
+template <bool STATS, bool STRICT, class CURSOR>
 __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constant__ FrameParams p) {
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
@@ -211,7 +286,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
         float sdy = (sg.y * ((floorf(ro.y) - ro.y) + 0.5f) + 0.5f) * tdy;
         float sdz = (sg.z * ((floorf(ro.z) - ro.z) + 0.5f) + 0.5f) * tdz;
 
-        GridCursor<BIG> cur(p, px, py, pz, sx, sy, sz);
+        CURSOR cur(p, px, py, pz, sx, sy, sz);
         const bool skip_empty = XN_DDA_SKIP_EMPTY && p.skip_empty != 0u; // volume has black background
 
         // texelFetch; outside the grid -> 0 (border)
@@ -338,6 +413,158 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
             st.step();
             st.read(4);
         }
+    }
+    store_result(p, ix, iy, acc.finish(ec), st);
+}
+
+// ---------------------------------------------------------------------------------
+// DDA over the texture residency (resources/dda.comp:13-73 again, same arithmetic).
+// The grid lives in a 3-D CUDA array; the texture unit does what the cursor code does for
+// the other layouts: address arithmetic (block-linear tiling, so a warp's texels share
+// sectors whatever the ray direction), the bounds test (border colour 0 = the reference's
+// clamp-to-border sampler, src/render/DdaRaytraceAlgorithm.cpp:26-29) and, in the fast
+// mode, the byte -> float conversion.  The voxel position is kept as three floats at texel
+// centres, stepped with predicated FADDs like the side distances.
+// ---------------------------------------------------------------------------------
+template <bool STRICT>
+struct TexFetch;
+template <>
+struct TexFetch<false> {
+    typedef float4 texel; // c / 255 per channel
+    static __device__ __forceinline__ texel fetch(const FrameParams& p, float x, float y, float z) {
+        return tex3D<float4>((cudaTextureObject_t)p.tex_unorm, x, y, z);
+    }
+    static __device__ __forceinline__ texel zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <>
+struct TexFetch<true> {
+    typedef uchar4 texel; // raw bytes
+    static __device__ __forceinline__ texel fetch(const FrameParams& p, float x, float y, float z) {
+        return tex3D<uchar4>((cudaTextureObject_t)p.tex_raw, x, y, z);
+    }
+    static __device__ __forceinline__ texel zero() { return make_uchar4(0, 0, 0, 0); }
+};
+
+// emission accumulator of the texture path: strict = shader order on exact c / 255,
+// fast = fma on the texture unit's c / 255 (scaled by the emission coefficient only)
+template <bool STRICT>
+struct TexAccum;
+template <>
+struct TexAccum<false> {
+    float r = 0.f, g = 0.f, b = 0.f;
+    __device__ __forceinline__ void add(float4 c, float len) {
+        r = __fmaf_rn(c.x, len, r);
+        g = __fmaf_rn(c.y, len, g);
+        b = __fmaf_rn(c.z, len, b);
+    }
+    __device__ __forceinline__ f3 finish(float ec) const { return F3(r * ec, g * ec, b * ec); }
+};
+template <>
+struct TexAccum<true> {
+    float r = 0.f, g = 0.f, b = 0.f;
+    __device__ __forceinline__ void add(uchar4 c, float len) {
+        r += unorm8_exact((float)c.x) * len;
+        g += unorm8_exact((float)c.y) * len;
+        b += unorm8_exact((float)c.z) * len;
+    }
+    __device__ __forceinline__ f3 finish(float ec) const { return F3(r * ec, g * ec, b * ec); }
+};
+
+template <bool STATS, bool STRICT>
+__global__ void __launch_bounds__(BLOCK_THREADS) dda_tex_kernel(const __grid_constant__ FrameParams p) {
+    typedef TexFetch<STRICT> TF;
+    typedef typename TF::texel texel;
+    uint32_t ix, iy;
+    thread_pixel(p, ix, iy);
+    if (ix >= p.out_w || iy >= p.out_h) return;
+    RayStats<STATS> st;
+
+    const f3 rd = make_ray(p, p.out_x + (int32_t)ix, p.out_y + (int32_t)iy);
+    const float side = fmaxf((float)p.nx, fmaxf((float)p.ny, (float)p.nz));
+    f3 ro = F3(p.pos[0] * side, p.pos[1] * side, p.pos[2] * side);
+    const float ec = voxel_emission_coeff(p, rd) / side;
+
+    const f3 rrd = F3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+    const f3 bias = F3(rrd.x * ro.x, rrd.y * ro.y, rrd.z * ro.z);
+    const f3 bmin = F3(-bias.x, -bias.y, -bias.z);
+    const f3 bmax = F3((float)p.model_dim[0] * rrd.x - bias.x, (float)p.model_dim[1] * rrd.y - bias.y,
+                       (float)p.model_dim[2] * rrd.z - bias.z);
+    float t_min = max_elem(F3(gmin(bmin.x, bmax.x), gmin(bmin.y, bmax.y), gmin(bmin.z, bmax.z)));
+    const float t_max = min_elem(F3(gmax(bmin.x, bmax.x), gmax(bmin.y, bmax.y), gmax(bmin.z, bmax.z)));
+
+    TexAccum<STRICT> acc;
+    if (!(t_min > t_max)) {
+        t_min = gmax(t_min, 0.0f);
+        ro = F3(ro.x + rd.x * t_min, ro.y + rd.y * t_min, ro.z + rd.z * t_min);
+        const float tdx = fabsf(rrd.x), tdy = fabsf(rrd.y), tdz = fabsf(rrd.z);
+        const f3 sg = F3(gsign(rd.x), gsign(rd.y), gsign(rd.z));
+        float sdx = (sg.x * ((floorf(ro.x) - ro.x) + 0.5f) + 0.5f) * tdx;
+        float sdy = (sg.y * ((floorf(ro.y) - ro.y) + 0.5f) + 0.5f) * tdy;
+        float sdz = (sg.z * ((floorf(ro.z) - ro.z) + 0.5f) + 0.5f) * tdz;
+        // ivec3(ro) truncates; texel centres are exact in binary32 (coordinates below 2^22)
+        float fx = (float)(int)ro.x + 0.5f, fy = (float)(int)ro.y + 0.5f, fz = (float)(int)ro.z + 0.5f;
+
+        texel v = TF::fetch(p, fx, fy, fz);
+        float t = 0.0f;
+        const float t_end = t_max - t_min;
+#define XN_TEX_STEP(DT)                                            \
+    {                                                              \
+        const float t0 = fminf(sdx, fminf(sdy, sdz));              \
+        const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0; \
+        DT = t0 - t;                                               \
+        t = t0;                                                    \
+        if (mx) { sdx += tdx; fx += sg.x; }                        \
+        if (my) { sdy += tdy; fy += sg.y; }                        \
+        if (mz) { sdz += tdz; fz += sg.z; }                        \
+        st.step();                                                 \
+        st.read(4);                                                \
+    }
+        // as in dda_kernel: while t < t_end - 4.5 td_min four more steps are certain, so they run
+        // as one trip whose four fetches are issued together and consumed one trip later
+        const float t_lim4 = t_end - 4.5f * fminf(tdx, fminf(tdy, tdz));
+        if (t < t_lim4) {
+            texel a0 = TF::zero(), a1 = TF::zero(), a2 = TF::zero(), a3 = v, b0, b1, b2, b3;
+            float ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, bd1, bd2, bd3;
+#define XN_TEX_TRIP(N, P)                                  \
+    {                                                      \
+        float d0;                                          \
+        XN_TEX_STEP(d0) N##0 = TF::fetch(p, fx, fy, fz);    \
+        XN_TEX_STEP(N##d1) N##1 = TF::fetch(p, fx, fy, fz); \
+        XN_TEX_STEP(N##d2) N##2 = TF::fetch(p, fx, fy, fz); \
+        XN_TEX_STEP(N##d3) N##3 = TF::fetch(p, fx, fy, fz); \
+        acc.add(P##0, P##d1);                              \
+        acc.add(P##1, P##d2);                              \
+        acc.add(P##2, P##d3);                              \
+        acc.add(P##3, d0);                                 \
+    }
+            for (;;) {
+                XN_TEX_TRIP(b, a)
+                if (!(t < t_lim4)) {
+                    acc.add(b0, bd1);
+                    acc.add(b1, bd2);
+                    acc.add(b2, bd3);
+                    v = b3;
+                    break;
+                }
+                XN_TEX_TRIP(a, b)
+                if (!(t < t_lim4)) {
+                    acc.add(a0, ad1);
+                    acc.add(a1, ad2);
+                    acc.add(a2, ad3);
+                    v = a3;
+                    break;
+                }
+            }
+#undef XN_TEX_TRIP
+        }
+        while (t < t_end) {
+            float dt;
+            XN_TEX_STEP(dt)
+            const texel vn = TF::fetch(p, fx, fy, fz);
+            acc.add(v, dt);
+            v = vn;
+        }
+#undef XN_TEX_STEP
     }
     store_result(p, ix, iy, acc.finish(ec), st);
 }
@@ -763,10 +990,19 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
     switch (traversal) {
         case 0:
             // XN_FORCE_IDX64=1 (test knob) runs the 64-bit-index kernel on small grids too
-            if ((uint64_t)p.nx * p.ny * p.nz < (1ull << 31) && !force_idx64())
-                dda_kernel<STATS, STRICT, false><<<grid, block, 0, stream>>>(p);
+            if (p.tex_unorm != 0ull) { // texture residency
+                dda_tex_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p);
+            } else if (p.bk_slots != 0) { // bricked residency (xn_brick.h)
+                if (p.bk_slots <= (1ull << 32) && !force_idx64())
+                    dda_kernel<STATS, STRICT, BrickCursor<false>><<<grid, block, 0, stream>>>(p);
+                else if (p.bk_top == 2u && p.bk_hs[2] <= 32u)
+                    dda_kernel<STATS, STRICT, BrickCursor<true>><<<grid, block, 0, stream>>>(p);
+                else
+                    return cudaErrorInvalidValue;
+            } else if ((uint64_t)p.nx * p.ny * p.nz < (1ull << 31) && !force_idx64())
+                dda_kernel<STATS, STRICT, GridCursor<false>><<<grid, block, 0, stream>>>(p);
             else
-                dda_kernel<STATS, STRICT, true><<<grid, block, 0, stream>>>(p);
+                dda_kernel<STATS, STRICT, GridCursor<true>><<<grid, block, 0, stream>>>(p);
             break;
         case 1: svo_naive_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p); break;
         case 2:

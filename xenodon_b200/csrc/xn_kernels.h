@@ -1,6 +1,7 @@
 // xn_kernels.h -- host-callable launchers of the device code in xn_kernels.cu
 #pragma once
 #include <cuda_runtime.h>
+#include "xn_brick.h"
 #include "xn_device.cuh"
 #include "xn_synth.h"
 
@@ -8,6 +9,10 @@ namespace xn {
 cudaError_t configure_kernels();
 cudaError_t launch_traversal(int traversal, const FrameParams& p, bool stats, bool strict, cudaStream_t stream);
 cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth, cudaStream_t stream);
+cudaError_t launch_brick_grid(const uint32_t* linear, uint32_t* bricked, const BrickLayout& L, uint32_t nx, uint32_t ny,
+                              uint32_t nz, cudaStream_t stream);
+cudaError_t launch_unbrick_grid(const uint32_t* bricked, uint32_t* linear, const BrickLayout& L, uint32_t nx,
+                                uint32_t ny, uint32_t nz, cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t stream);
 cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride, unsigned long long* out,
                                cudaStream_t stream);

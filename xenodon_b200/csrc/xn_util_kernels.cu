@@ -1,4 +1,5 @@
 // xn_util_kernels.cu -- volume re-layout, synthetic-volume and statistics kernels (sm_100a).
+#include "xn_brick.h"
 #include "xn_device.cuh"
 #include "xn_kernels.h"
 #include "xn_synth.h"
@@ -39,6 +40,43 @@ cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint3
     const int threads = 256;
     const uint64_t blocks = (count + threads - 1) / threads;
     relayout_nodes_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, out, d_max_depth);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// grid re-layout: x-major linear <-> bricked (xn_brick.h).  One thread per bricked slot, so the
+// bricked side is accessed in order; the linear side is touched in 2x2x2 / 4x4x2 groups that
+// stay inside a few cache lines.  Padding slots are written as 0 (= the border colour).
+// ---------------------------------------------------------------------------------
+__global__ void brick_grid_kernel(const uint32_t* __restrict__ linear, uint32_t* __restrict__ bricked, BrickLayout L,
+                                  uint32_t nx, uint32_t ny, uint32_t nz) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = brick_coord(L, 0, i), y = brick_coord(L, 1, i), z = brick_coord(L, 2, i);
+        uint32_t v = 0;
+        if (x < nx && y < ny && z < nz) v = linear[(uint64_t)x + (uint64_t)y * nx + (uint64_t)z * nx * ny];
+        bricked[i] = v;
+    }
+}
+
+__global__ void unbrick_grid_kernel(const uint32_t* __restrict__ bricked, uint32_t* __restrict__ linear, BrickLayout L,
+                                    uint32_t nx, uint32_t ny, uint32_t nz) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = brick_coord(L, 0, i), y = brick_coord(L, 1, i), z = brick_coord(L, 2, i);
+        if (x < nx && y < ny && z < nz) linear[(uint64_t)x + (uint64_t)y * nx + (uint64_t)z * nx * ny] = bricked[i];
+    }
+}
+
+cudaError_t launch_brick_grid(const uint32_t* linear, uint32_t* bricked, const BrickLayout& L, uint32_t nx, uint32_t ny,
+                              uint32_t nz, cudaStream_t stream) {
+    brick_grid_kernel<<<148 * 16, 256, 0, stream>>>(linear, bricked, L, nx, ny, nz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unbrick_grid(const uint32_t* bricked, uint32_t* linear, const BrickLayout& L, uint32_t nx,
+                                uint32_t ny, uint32_t nz, cudaStream_t stream) {
+    unbrick_grid_kernel<<<148 * 16, 256, 0, stream>>>(bricked, linear, L, nx, ny, nz);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libxenodon_b200.so")
+# XN_LIBRARY: an alternative build of the same library (tuning A/B runs, xenodon_b200.build --variant)
+LIB_PATH = os.environ.get("XN_LIBRARY") or os.path.join(_PKG, "libxenodon_b200.so")
 CLI_PATH = os.path.join(_PKG, "bin", "xenodon")
 
 DDA, SVO_NAIVE, ESVO, SVO_DF, SVO_ROPE = range(5)

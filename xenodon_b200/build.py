@@ -104,5 +104,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defs: str) -> str:
+    """A/B experiments: libxenodon_b200 with xn_kernels.cu recompiled under extra -D flags, written to
+    xenodon_b200/variants/libxenodon_b200_<name>.so (selected at run time with XN_LIBRARY=<path>)."""
+    build()
+    vdir = os.path.join(PKG, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    nvcc, gxx = _nvcc(), _gxx()
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    obj = os.path.join(OBJ, f"xn_kernels_{name}.o")
+    _run([nvcc, "-ccbin", gxx, *ARCH, *NVCC_KERNEL_FLAGS, *defs.split(), *inc, "-c", os.path.join(CSRC, "xn_kernels.cu"),
+          "-o", obj])
+    others = [os.path.join(OBJ, src.replace("/", "_") + ".o") for src, _ in CU_SOURCES if src != "xn_kernels.cu"]
+    others += [os.path.join(OBJ, src.replace("/", "_") + ".o") for src in CPP_SOURCES]
+    out = os.path.join(vdir, f"libxenodon_b200_{name}.so")
+    _run([nvcc, "-ccbin", gxx, *ARCH, "-shared", "-o", out, obj, *others, "-lz", "-Xlinker", "--no-undefined"])
+    return out
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:  # python -m xenodon_b200.build --variant NAME "-DXN_FOO=1 ..."
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2] if len(sys.argv) > i + 2 else ""))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose=True))

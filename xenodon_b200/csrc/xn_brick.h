@@ -21,9 +21,9 @@
 #include <cstdint>
 
 #ifdef __CUDACC__
-#define XN_HD __host__ __device__ __forceinline__
+#define XN_BRICK_HD __host__ __device__ __forceinline__
 #else
-#define XN_HD inline
+#define XN_BRICK_HD inline
 #endif
 
 namespace xn {
@@ -36,23 +36,23 @@ struct BrickLayout {
     uint64_t total;   // number of voxel slots including padding
 };
 
-XN_HD uint32_t brick_m3(uint32_t a) { return (a & 1u) | ((a & 2u) << 2) | ((a & 4u) << 4); }
-XN_HD uint32_t brick_c3(uint64_t v) {
+XN_BRICK_HD uint32_t brick_m3(uint32_t a) { return (a & 1u) | ((a & 2u) << 2) | ((a & 4u) << 4); }
+XN_BRICK_HD uint32_t brick_c3(uint64_t v) {
     return (uint32_t)((v & 1u) | ((v >> 2) & 2u) | ((v >> 4) & 4u));
 }
 
 // dilated coordinate of c on `axis`; consistent with the step arithmetic for the out-of-range
 // values -1 and n (they wrap inside the axis' own bits)
-XN_HD uint64_t brick_axis(const BrickLayout& L, int axis, int64_t c) {
+XN_BRICK_HD uint64_t brick_axis(const BrickLayout& L, int axis, int64_t c) {
     const uint64_t lo = (uint64_t)brick_m3((uint32_t)c & 7u) << axis;
     const uint64_t hi = ((uint64_t)(c >> 3) << L.hs[axis]);
     return (lo | hi) & L.mask[axis];
 }
-XN_HD uint64_t brick_index(const BrickLayout& L, uint32_t x, uint32_t y, uint32_t z) {
+XN_BRICK_HD uint64_t brick_index(const BrickLayout& L, uint32_t x, uint32_t y, uint32_t z) {
     return brick_axis(L, 0, x) | brick_axis(L, 1, y) | brick_axis(L, 2, z);
 }
 // coordinate on `axis` of index i
-XN_HD uint32_t brick_coord(const BrickLayout& L, int axis, uint64_t i) {
+XN_BRICK_HD uint32_t brick_coord(const BrickLayout& L, int axis, uint64_t i) {
     const uint64_t field = (i & L.mask[axis]) >> L.hs[axis];
     return (uint32_t)(field << 3) | brick_c3(i >> axis);
 }

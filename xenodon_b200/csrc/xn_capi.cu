@@ -93,8 +93,9 @@ struct xn_ctx {
     cudaTextureObject_t tex_unorm = 0, tex_raw = 0;
     int layout_mode = XN_GRID_LAYOUT_AUTO;
     uint64_t nx = 0, ny = 0, nz = 0;
-    xn::DNode* nodes = nullptr;
-    uint64_t node_count = 0, side = 0;
+    xn::DNode* nodes = nullptr;  // file-order 64-byte records (svo_rope)
+    xn::CNode* cnodes = nullptr; // compact level-order records of the internal nodes (the other three)
+    uint64_t node_count = 0, internal_count = 0, side = 0;
     uint32_t root_meta = 0, max_depth = 0;
     bool grid_has_black_background = false;
 
@@ -134,8 +135,10 @@ struct xn_ctx {
     bool have_grid() const { return grid || bricks || tex_array; }
     void free_nodes() {
         if (nodes) cudaFree(nodes);
+        if (cnodes) cudaFree(cnodes);
         nodes = nullptr;
-        node_count = side = 0;
+        cnodes = nullptr;
+        node_count = internal_count = side = 0;
     }
 };
 
@@ -200,6 +203,7 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.ny = (uint32_t)ctx->ny;
     p.nz = (uint32_t)ctx->nz;
     p.nodes = ctx->nodes;
+    p.cnodes = ctx->cnodes;
     p.root_meta = ctx->root_meta;
     p.max_depth = ctx->max_depth;
     p.il_count = ctx->il_count;
@@ -341,6 +345,7 @@ void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) 
     XN_CUDA(cudaMalloc(&d_max, sizeof(uint32_t)));
     XN_CUDA(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), ctx->stream));
     XN_CUDA(xn::launch_relayout(d_raw, count, ctx->nodes, d_max, ctx->stream));
+    XN_CUDA(xn::build_compact_nodes(d_raw, count, &ctx->cnodes, &ctx->internal_count, ctx->stream));
     uint32_t root[2] = {0, 0};
     XN_CUDA(cudaMemcpyAsync(root, (const uint8_t*)d_raw + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
     uint32_t maxd = 0;

@@ -25,6 +25,19 @@ struct __align__(64) DNode {
 };
 static_assert(sizeof(DNode) == 64, "device node must be 64 bytes");
 
+// Compact octree residency read by svo_naive / svo_df / esvo: INTERNAL nodes only, 32 bytes
+// (one sector) each, numbered level by level (root = 0, then depth 1, ...; file order inside a
+// level), so the upper levels are one contiguous range that an L2 access-policy window keeps
+// resident.  One 32-bit word per child:
+//   leaf child     : bit 31 set | depth << 24 | b << 16 | g << 8 | r   (the same bits as `meta`)
+//   internal child : its compact index (bit 31 clear)
+// A leaf's own node record is never read by these three traversals (everything they need about a
+// leaf is in its parent's word), so leaves -- 7/8 of a tree -- occupy no space here.
+struct __align__(32) CNode {
+    uint32_t w[8];
+};
+static_assert(sizeof(CNode) == 32, "compact node must be 32 bytes");
+
 constexpr uint32_t META_LEAF = 0x80000000u;
 __host__ __device__ inline uint32_t make_meta(uint32_t color, uint32_t is_leaf_depth) {
     return (is_leaf_depth & META_LEAF) | ((is_leaf_depth & 0x1Fu) << 24) | (color & 0x00FFFFFFu);
@@ -58,7 +71,8 @@ struct FrameParams {
     // texture residency: the grid as a 3-D CUDA array (block-linear tiling, border = 0) seen through
     // two texture objects: channels as c / 255 floats (fast mode) and as raw bytes (strict mode)
     unsigned long long tex_unorm, tex_raw;
-    const DNode* nodes;
+    const DNode* nodes;   // svo_rope (and the file-order view of the tree)
+    const CNode* cnodes;  // svo_naive, svo_df, esvo
     uint32_t root_meta;
     uint32_t max_depth;     // deepest node depth in the tree (stack sizing)
 

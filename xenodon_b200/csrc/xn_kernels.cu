@@ -40,6 +40,10 @@
 #ifndef XN_DDA_SEGMENTS
 #define XN_DDA_SEGMENTS 1
 #endif
+// ESVO POP: 1 = differing bits from the old/new positions and mask-based truncation
+#ifndef XN_ESVO_POP
+#define XN_ESVO_POP 0
+#endif
 
 namespace xn {
 
@@ -245,6 +249,51 @@ struct BrickCursor<true> {
     }
 };
 
+// One DDA step (dda.comp:41-50): t0 = min(side distances), dt = t0 - t, every axis whose side
+// distance equals t0 steps.  Generic form in C++; for the 32-bit linear cursor the step is written
+// in PTX with predicated adds, because the compiler otherwise turns the three conditional index
+// updates into SEL + three-input adds -- five ALU-pipe instructions on the pipe that bounds this
+// kernel (ncu: ALU 69 %) instead of three predicated adds.
+#ifndef XN_DDA_PTX_STEP
+#define XN_DDA_PTX_STEP 1
+#endif
+template <class CURSOR>
+__device__ __forceinline__ void dda_step(CURSOR& cur, float& sdx, float& sdy, float& sdz, float tdx, float tdy,
+                                         float tdz, float& t, float& dt) {
+    const float t0 = fminf(sdx, fminf(sdy, sdz));
+    const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0;
+    dt = t0 - t;
+    t = t0;
+    if (mx) { sdx += tdx; cur.step_x(); }
+    if (my) { sdy += tdy; cur.step_y(); }
+    if (mz) { sdz += tdz; cur.step_z(); }
+}
+#if XN_DDA_PTX_STEP
+template <>
+__device__ __forceinline__ void dda_step<GridCursor<false>>(GridCursor<false>& cur, float& sdx, float& sdy, float& sdz,
+                                                            float tdx, float tdy, float tdz, float& t, float& dt) {
+    asm("{\n\t"
+        ".reg .pred px, py, pz;\n\t"
+        ".reg .f32 t0;\n\t"
+        "min.f32 t0, %1, %2;\n\t"
+        "min.f32 t0, %0, t0;\n\t"
+        "setp.eq.f32 px, %0, t0;\n\t"
+        "setp.eq.f32 py, %1, t0;\n\t"
+        "setp.eq.f32 pz, %2, t0;\n\t"
+        "sub.f32 %5, t0, %4;\n\t"
+        "mov.f32 %4, t0;\n\t"
+        "@px add.f32 %0, %0, %6;\n\t"
+        "@py add.f32 %1, %1, %7;\n\t"
+        "@pz add.f32 %2, %2, %8;\n\t"
+        "@px add.s32 %3, %3, %9;\n\t"
+        "@py add.s32 %3, %3, %10;\n\t"
+        "@pz add.s32 %3, %3, %11;\n\t"
+        "}"
+        : "+f"(sdx), "+f"(sdy), "+f"(sdz), "+r"(cur.idx), "+f"(t), "=f"(dt)
+        : "f"(tdx), "f"(tdy), "f"(tdz), "r"(cur.dix), "r"(cur.diy), "r"(cur.diz));
+}
+#endif
+
 // ---------------------------------------------------------------------------------
 // DDA (resources/dda.comp:13-73)
 // CURSOR selects the resident layout and index width: GridCursor<false/true> = x-major linear
@@ -322,17 +371,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
                         // and only then accumulates the four texels requested by the PREVIOUS trip,
                         // so a load has a whole trip to arrive (two register sets, a / b).
                         const float t_lim4 = t_lim - 4.5f * fminf(tdx, fminf(tdy, tdz));
-#define XN_DDA_STEP(DT)                                            \
-    {                                                              \
-        const float t0 = fminf(sdx, fminf(sdy, sdz));              \
-        const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0; \
-        DT = t0 - t;                                               \
-        t = t0;                                                    \
-        if (mx) { sdx += tdx; cur.step_x(); }                      \
-        if (my) { sdy += tdy; cur.step_y(); }                      \
-        if (mz) { sdz += tdz; cur.step_z(); }                      \
-        st.step();                                                 \
-        st.read(4);                                                \
+#define XN_DDA_STEP(DT)                                        \
+    {                                                          \
+        dda_step(cur, sdx, sdy, sdz, tdx, tdy, tdz, t, DT);    \
+        st.step();                                             \
+        st.read(4);                                            \
     }
 #define XN_DDA_TRIP(N, P)                                                        \
     {                                                                            \
@@ -597,6 +640,19 @@ __device__ __forceinline__ uint2 stack_load(uint32_t base, uint32_t level) {
 __device__ __forceinline__ uint2 load_slot(const DNode* __restrict__ nodes, uint32_t node, uint32_t child) {
     return __ldg(&nodes[node].slot[child]);
 }
+// compact residency: one word per child (leaf: meta bits, internal: compact child index)
+__device__ __forceinline__ uint32_t load_word(const CNode* __restrict__ nodes, uint32_t node, uint32_t child) {
+    return __ldg(&nodes[node].w[child]);
+}
+__device__ __forceinline__ bool word_is_leaf(uint32_t w) { return (int32_t)w < 0; }
+// child descriptor as (index, meta) from either residency
+__device__ __forceinline__ uint2 load_child(const DNode* __restrict__ nodes, uint32_t node, uint32_t child) {
+    return load_slot(nodes, node, child);
+}
+__device__ __forceinline__ uint2 load_child(const CNode* __restrict__ nodes, uint32_t node, uint32_t child) {
+    const uint32_t w = load_word(nodes, node, child);
+    return make_uint2(w, w); // leaf: .y carries flag + colour; internal: .x is the index, .y has bit 31 clear
+}
 
 // slab test of the unit cube [0,1]^3 (svo_naive.comp:30-45, svo_rope.comp:72-86)
 __device__ __forceinline__ bool unit_cube_slab(f3 rrd, f3 bias, float& t_min, float& t_max) {
@@ -611,8 +667,8 @@ __device__ __forceinline__ bool unit_cube_slab(f3 rrd, f3 bias, float& t_min, fl
 
 // descend from (node, meta) at `offset`/`extent` to the leaf containing pos
 // (loop body of find(), svo_naive.comp:14-26 == svo_rope.comp:14-26 == svo_rope.comp:33-47)
-template <bool STATS>
-__device__ __forceinline__ void descend(const DNode* __restrict__ nodes, f3 pos, uint32_t& node, uint32_t& meta,
+template <bool STATS, class NODE>
+__device__ __forceinline__ void descend(const NODE* __restrict__ nodes, f3 pos, uint32_t& node, uint32_t& meta,
                                         f3& offset, float& extent, RayStats<STATS>& st) {
     for (;;) {
         st.read(4); // is_leaf_depth
@@ -627,7 +683,7 @@ __device__ __forceinline__ void descend(const DNode* __restrict__ nodes, f3 pos,
         if (my) offset.y += extent;
         if (mz) offset.z += extent;
         st.read(4); // children[child]
-        const uint2 s = load_slot(nodes, node, child);
+        const uint2 s = load_child(nodes, node, child);
         node = s.x;
         meta = s.y;
     }
@@ -669,7 +725,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_naive_ke
             uint32_t node = 0, meta = p.root_meta;
             f3 offset = F3(0.f, 0.f, 0.f);
             float side = 1.0f;
-            descend(p.nodes, pt, node, meta, offset, side, st);
+            descend(p.cnodes, pt, node, meta, offset, side, st);
 
             float u_min, u_max;
             f3 far;
@@ -714,7 +770,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
     for (;;) {
         st.step();
         st.read(4); // children[child_idx]
-        const uint2 s = load_slot(p.nodes, node, child_idx);
+        const uint32_t s = load_word(p.cnodes, node, child_idx);
         const f3 bmin = F3(pos.x * rrd.x - bias.x, pos.y * rrd.y - bias.y, pos.z * rrd.z - bias.z);
         const f3 bmax = F3((pos.x + side) * rrd.x - bias.x, (pos.y + side) * rrd.y - bias.y,
                            (pos.z + side) * rrd.z - bias.z);
@@ -723,17 +779,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
 
         if (t_min < t_max && t_max > 0.0f) {
             st.read(4); // nodes[child].is_leaf_depth
-            if (meta_is_leaf(s.y)) {
+            if (word_is_leaf(s)) {
                 st.read(4); // color
-                acc.add(s.y, t_max - gmax(t_min, 0.0f));
+                acc.add(s, t_max - gmax(t_min, 0.0f));
             } else {
                 if (child_idx != 7u) {
                     if (sp < LEVELS) stack_store(stack, (uint32_t)sp, node, child_idx | (depth << 3));
                     ++sp;
                 }
                 side *= 0.5f;
-                node = s.x;
-                depth = meta_depth(s.y);
+                node = s;
+                ++depth; // a child is one level below its parent (also in DAGs: shared subtrees have one size)
                 child_idx = 0;
                 continue;
             }
@@ -761,6 +817,74 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
         if (child_idx & 1u) pos.z += side;
     }
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
+}
+
+// ESVO child selection written with predicated PTX (as dda_step): the compiler turns
+// `if (c) { pos += d; idx ^= bit; }` into compare + FADD + FSEL + SEL chains on the ALU pipe,
+// which bounds this kernel (ncu: ALU 70 %, issue 72 %); predicated FADDs run on the FMA pipe.
+#ifndef XN_ESVO_PTX
+#define XN_ESVO_PTX 0
+#endif
+// ADVANCE (esvo.comp:96-104): axes whose corner time equals tc_max step back by `se`;
+// returns the step mask (x = 4, y = 2, z = 1)
+__device__ __forceinline__ uint32_t esvo_advance(float tcorx, float tcory, float tcorz, float tc_max, float se,
+                                                 float& posx, float& posy, float& posz) {
+#if XN_ESVO_PTX
+    uint32_t m;
+    asm("{\n\t"
+        ".reg .pred ax, ay, az;\n\t"
+        ".reg .b32 mx, my, mz;\n\t"
+        "setp.le.f32 ax, %4, %7;\n\t"
+        "setp.le.f32 ay, %5, %7;\n\t"
+        "setp.le.f32 az, %6, %7;\n\t"
+        "@ax sub.f32 %1, %1, %8;\n\t"
+        "@ay sub.f32 %2, %2, %8;\n\t"
+        "@az sub.f32 %3, %3, %8;\n\t"
+        "selp.b32 mx, 4, 0, ax;\n\t"
+        "selp.b32 my, 2, 0, ay;\n\t"
+        "selp.b32 mz, 1, 0, az;\n\t"
+        "lop3.b32 %0, mx, my, mz, 0xFE;\n\t"
+        "}"
+        : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
+        : "f"(tcorx), "f"(tcory), "f"(tcorz), "f"(tc_max), "f"(se));
+    return m;
+#else
+    const bool ax = tcorx <= tc_max, ay = tcory <= tc_max, az = tcorz <= tc_max;
+    if (ax) posx -= se;
+    if (ay) posy -= se;
+    if (az) posz -= se;
+    return (ax ? 4u : 0u) | (ay ? 2u : 0u) | (az ? 1u : 0u);
+#endif
+}
+// PUSH child selection (esvo.comp:84-90): the half of the node the ray enters first on every axis
+__device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, float tcenz, float t_min, float se,
+                                                     float& posx, float& posy, float& posz) {
+#if XN_ESVO_PTX
+    uint32_t m;
+    asm("{\n\t"
+        ".reg .pred ax, ay, az;\n\t"
+        ".reg .b32 mx, my, mz;\n\t"
+        "setp.gt.f32 ax, %4, %7;\n\t"
+        "setp.gt.f32 ay, %5, %7;\n\t"
+        "setp.gt.f32 az, %6, %7;\n\t"
+        "@ax add.f32 %1, %1, %8;\n\t"
+        "@ay add.f32 %2, %2, %8;\n\t"
+        "@az add.f32 %3, %3, %8;\n\t"
+        "selp.b32 mx, 4, 0, ax;\n\t"
+        "selp.b32 my, 2, 0, ay;\n\t"
+        "selp.b32 mz, 1, 0, az;\n\t"
+        "lop3.b32 %0, mx, my, mz, 0xFE;\n\t"
+        "}"
+        : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
+        : "f"(tcenx), "f"(tceny), "f"(tcenz), "f"(t_min), "f"(se));
+    return m;
+#else
+    uint32_t m = 0;
+    if (tcenx > t_min) { m ^= 4u; posx += se; }
+    if (tceny > t_min) { m ^= 2u; posy += se; }
+    if (tcenz > t_min) { m ^= 1u; posz += se; }
+    return m;
+#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -813,12 +937,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
 
     Accum<STRICT> acc;
     const uint32_t stack = stack_base(stack_mem);
-    const DNode* __restrict__ nodes = p.nodes;
+    const CNode* __restrict__ nodes = p.cnodes;
 
     // The child descriptor of (parent, idx) is requested at the END of the previous iteration,
     // at a single load site (99.6 % of iterations consume it, ncu r01), so the t_corner
     // arithmetic of the next iteration overlaps the load instead of waiting behind it.
-    uint2 s = load_slot(nodes, parent, idx ^ octant_mask);
+    uint32_t s = load_word(nodes, parent, idx ^ octant_mask);
 
     while (scale < cast_stack_depth) {
         st.step();
@@ -826,13 +950,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
         const float tc_max = fminf(tcorx, fminf(tcory, tcorz));
 
         bool pushed = false;
-        if (t_min <= t_max) {
+        {
+            // esvo.comp:70-72 tests t_min <= t_max, then t_min <= tv_max = min(t_max, tc_max); the
+            // second test implies the first (no NaNs on this path), so one comparison decides
             const float tv_max = fminf(t_max, tc_max);
             if (t_min <= tv_max) {
                 st.read(8); // children[idx ^ octant_mask] + nodes[child].is_leaf_depth
-                if (meta_is_leaf(s.y)) {
+                if (word_is_leaf(s)) {
                     st.read(4); // color
-                    acc.add(s.y, tv_max - t_min);
+                    acc.add(s, tv_max - t_min);
                 } else {
                     // PUSH
                     if (tc_max < h) {
@@ -840,15 +966,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
                         if (level < (uint32_t)LEVELS) stack_store(stack, level, parent, __float_as_uint(t_max));
                     }
                     h = tc_max;
-                    parent = s.x;
+                    parent = s;
                     --scale;
                     scale_exp2 *= 0.5f;
                     const float tcenx = scale_exp2 * tcx + tcorx, tceny = scale_exp2 * tcy + tcory,
                                 tcenz = scale_exp2 * tcz + tcorz;
-                    idx = 0;
-                    if (tcenx > t_min) { idx ^= 4u; posx += scale_exp2; }
-                    if (tceny > t_min) { idx ^= 2u; posy += scale_exp2; }
-                    if (tcenz > t_min) { idx ^= 1u; posz += scale_exp2; }
+                    idx = esvo_first_child(tcenx, tceny, tcenz, t_min, scale_exp2, posx, posy, posz);
                     t_max = tv_max;
                     pushed = true;
                 }
@@ -857,20 +980,28 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
 
         if (!pushed) {
             // ADVANCE
-            const bool ax = tcorx <= tc_max, ay = tcory <= tc_max, az = tcorz <= tc_max;
-            const uint32_t step_mask = (ax ? 4u : 0u) | (ay ? 2u : 0u) | (az ? 1u : 0u);
-            if (ax) posx -= scale_exp2;
-            if (ay) posy -= scale_exp2;
-            if (az) posz -= scale_exp2;
+#if XN_ESVO_POP
+            const float ox = posx, oy = posy, oz = posz;
+#endif
+            const uint32_t step_mask = esvo_advance(tcorx, tcory, tcorz, tc_max, scale_exp2, posx, posy, posz);
+            const bool ax = (step_mask & 4u) != 0u, ay = (step_mask & 2u) != 0u, az = (step_mask & 1u) != 0u;
             t_min = tc_max;
             idx ^= step_mask;
 
             if ((idx & step_mask) != 0u) {
                 // POP
+#if XN_ESVO_POP
+                // pos + scale_exp2 is the position before the step, exactly; axes that did not
+                // step contribute 0 (esvo.comp:108-116)
+                const uint32_t dbits = (__float_as_uint(ox) ^ __float_as_uint(posx)) |
+                                       (__float_as_uint(oy) ^ __float_as_uint(posy)) |
+                                       (__float_as_uint(oz) ^ __float_as_uint(posz));
+#else
                 uint32_t dbits = 0;
                 if (ax) dbits |= __float_as_uint(posx) ^ __float_as_uint(posx + scale_exp2);
                 if (ay) dbits |= __float_as_uint(posy) ^ __float_as_uint(posy + scale_exp2);
                 if (az) dbits |= __float_as_uint(posz) ^ __float_as_uint(posz + scale_exp2);
+#endif
                 // esvo.comp:117 takes the exponent of float(dbits); dbits is a union of carry runs
                 // of at most 23 bits inside the cube (exact in binary32), so the index of its
                 // highest set bit is the same number, and anything >= 23 (or dbits == 0) leaves
@@ -884,14 +1015,21 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
                 t_max = __uint_as_float(e.y);
                 const uint32_t shx = __float_as_uint(posx) >> scale, shy = __float_as_uint(posy) >> scale,
                                shz = __float_as_uint(posz) >> scale;
+#if XN_ESVO_POP
+                const uint32_t keep = 0xFFFFFFFFu << scale;
+                posx = __uint_as_float(__float_as_uint(posx) & keep);
+                posy = __uint_as_float(__float_as_uint(posy) & keep);
+                posz = __uint_as_float(__float_as_uint(posz) & keep);
+#else
                 posx = __uint_as_float(shx << scale);
                 posy = __uint_as_float(shy << scale);
                 posz = __uint_as_float(shz << scale);
+#endif
                 idx = (shx & 1u) * 4u + (shy & 1u) * 2u + (shz & 1u);
                 h = 0.0f;
             }
         }
-        s = load_slot(nodes, parent, idx ^ octant_mask);
+        s = load_word(nodes, parent, idx ^ octant_mask);
     }
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
 }

@@ -9,6 +9,9 @@ namespace xn {
 cudaError_t configure_kernels();
 cudaError_t launch_traversal(int traversal, const FrameParams& p, bool stats, bool strict, cudaStream_t stream);
 cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth, cudaStream_t stream);
+// compact residency of the octree (internal nodes only, level order); *out is cudaMalloc'ed
+cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, uint64_t* n_internal_out,
+                                cudaStream_t stream);
 cudaError_t launch_brick_grid(const uint32_t* linear, uint32_t* bricked, const BrickLayout& L, uint32_t nx, uint32_t ny,
                               uint32_t nz, cudaStream_t stream);
 cudaError_t launch_unbrick_grid(const uint32_t* bricked, uint32_t* linear, const BrickLayout& L, uint32_t nx,

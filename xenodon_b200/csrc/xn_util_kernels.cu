@@ -1,4 +1,6 @@
 // xn_util_kernels.cu -- volume re-layout, synthetic-volume and statistics kernels (sm_100a).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "xn_brick.h"
 #include "xn_device.cuh"
 #include "xn_kernels.h"
@@ -41,6 +43,97 @@ cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint3
     const uint64_t blocks = (count + threads - 1) / threads;
     relayout_nodes_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, out, d_max_depth);
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// compact octree residency (CNode, xn_device.cuh): internal nodes only, level order.
+//   1. key = depth for internal nodes (root forced to 0), 31 for leaves; stable radix sort of
+//      the node indices by key  ->  level order with file order inside a level, leaves last;
+//   2. rank[file index] = position in that order (the compact index);
+//   3. one thread per internal node writes its eight child words.
+// ---------------------------------------------------------------------------------
+__global__ void compact_keys_kernel(const uint32_t* __restrict__ raw, uint64_t count, uint8_t* __restrict__ keys,
+                                    uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_internal) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned internal = 0;
+    if (i < count) {
+        const uint32_t ld = raw[i * 10u + 9u];
+        const bool leaf = (ld & 0x80000000u) != 0u;
+        internal = (i == 0 || !leaf) ? 1u : 0u; // the root always has a record (a leaf root points at itself)
+        keys[i] = i == 0 ? 0 : (leaf ? 31 : (uint8_t)min(ld & 0x7FFFFFFFu, 30u));
+        vals[i] = (uint32_t)i;
+    }
+    const unsigned n = __popc(__ballot_sync(0xFFFFFFFFu, internal != 0u));
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(n_internal, (unsigned long long)n);
+}
+
+__global__ void compact_rank_kernel(const uint32_t* __restrict__ order, uint64_t n_internal, uint32_t* __restrict__ rank) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_internal) rank[order[j]] = (uint32_t)j;
+}
+
+__global__ void compact_emit_kernel(const uint32_t* __restrict__ raw, uint64_t count, const uint32_t* __restrict__ order,
+                                    const uint32_t* __restrict__ rank, uint64_t n_internal, CNode* __restrict__ out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_internal) return;
+    const uint32_t* n = raw + (uint64_t)order[j] * 10u;
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t child = n[c];
+        if (child >= count) child = 0; // malformed file: never index out of bounds
+        const uint32_t* cn = raw + (uint64_t)child * 10u;
+        w[c] = (cn[9] & 0x80000000u) ? make_meta(cn[8], cn[9]) : rank[child];
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + j);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, uint64_t* n_internal_out,
+                                cudaStream_t stream) {
+    *out = nullptr;
+    uint8_t *k_in = nullptr, *k_out = nullptr;
+    uint32_t *v_in = nullptr, *v_out = nullptr, *rank = nullptr;
+    unsigned long long* d_n = nullptr;
+    void* tmp = nullptr;
+    CNode* nodes = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto done = [&](cudaError_t err) {
+        cudaFree(k_in), cudaFree(k_out), cudaFree(v_in), cudaFree(v_out), cudaFree(rank), cudaFree(d_n), cudaFree(tmp);
+        if (err != cudaSuccess && nodes) cudaFree(nodes);
+        return err;
+    };
+#define XN_TRY(call) if ((e = (call)) != cudaSuccess) return done(e)
+    XN_TRY(cudaMalloc(&k_in, count));
+    XN_TRY(cudaMalloc(&k_out, count));
+    XN_TRY(cudaMalloc(&v_in, count * 4));
+    XN_TRY(cudaMalloc(&v_out, count * 4));
+    XN_TRY(cudaMalloc(&rank, count * 4));
+    XN_TRY(cudaMalloc(&d_n, 8));
+    XN_TRY(cudaMemsetAsync(d_n, 0, 8, stream));
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((count + threads - 1) / threads);
+    compact_keys_kernel<<<blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, k_in, v_in, d_n);
+    XN_TRY(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    XN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)count, 0, 5, stream));
+    XN_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    XN_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)count, 0, 5, stream));
+    unsigned long long n_internal = 0;
+    XN_TRY(cudaMemcpyAsync(&n_internal, d_n, 8, cudaMemcpyDeviceToHost, stream));
+    XN_TRY(cudaStreamSynchronize(stream));
+    XN_TRY(cudaMalloc(&nodes, n_internal * sizeof(CNode)));
+    const unsigned iblocks = (unsigned)((n_internal + threads - 1) / threads);
+    compact_rank_kernel<<<iblocks, threads, 0, stream>>>(v_out, n_internal, rank);
+    XN_TRY(cudaGetLastError());
+    compact_emit_kernel<<<iblocks, threads, 0, stream>>>((const uint32_t*)raw40, count, v_out, rank, n_internal, nodes);
+    XN_TRY(cudaGetLastError());
+    XN_TRY(cudaStreamSynchronize(stream));
+#undef XN_TRY
+    *out = nodes;
+    *n_internal_out = n_internal;
+    return done(cudaSuccess);
 }
 
 // ---------------------------------------------------------------------------------

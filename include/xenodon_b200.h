@@ -102,6 +102,13 @@ XN_API int xn_ctx_device(const xn_ctx* ctx);
  * The caller keeps ownership of the host arrays and may free them after return. */
 XN_API int xn_upload_grid(xn_ctx* ctx, const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz);
 XN_API int xn_upload_svo(xn_ctx* ctx, const xn_node* nodes, uint64_t count, uint64_t side);
+/* Grid::load_tiff + DdaRaytraceResources in one pipelined step (src/model/Grid.cpp:27-79,
+ * src/render/DdaRaytraceAlgorithm.cpp:49-96): z slices are read into page-locked staging buffers
+ * by worker threads and decoded on the device (sample expansion, alpha pre-multiplication,
+ * bottom-up rows) straight into the resident grid, so no host copy of the volume exists and disk
+ * reads overlap the transfers.  The resident voxels equal xn_tiff_read + xn_upload_grid byte for
+ * byte.  dims_out (nullable) receives nx, ny, nz; seconds_out (nullable) the wall time. */
+XN_API int xn_upload_grid_tiff(xn_ctx* ctx, const char* path, uint64_t dims_out[3], double* seconds_out);
 /* same, from memory already resident on ctx's device (copied device-to-device) */
 XN_API int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t ny, uint64_t nz);
 XN_API int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uint64_t side);

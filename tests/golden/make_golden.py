@@ -100,6 +100,15 @@ def main():
             ims = [Image.fromarray(arr[z], mode) for z in range(arr.shape[0])]
             ims[0].save(path, save_all=True, append_images=ims[1:], big_tiff=big)
             tiff[name] = xref_model.load_tiff(path)
+    # ... and hand-written files covering every sample layout (grey / grey+alpha / RGB / RGBA with
+    # each ExtraSamples value): libtiff pre-multiplies only unassociated RGB, and ignores a grey
+    # image's second sample unless ExtraSamples declares it alpha
+    sys.path.insert(0, os.path.dirname(HERE))
+    from util import TIFF_LAYOUTS, tiff_layout_name, write_tiff_layout
+    for spp, phot, extra in TIFF_LAYOUTS:
+        name = tiff_layout_name(spp, phot, extra)
+        write_tiff_layout(os.path.join(HERE, name), spp, phot, extra)
+        tiff[name] = xref_model.load_tiff(os.path.join(HERE, name))
     np.savez_compressed(os.path.join(HERE, "tiff_golden.npz"), **tiff)
     print("golden fixtures written to", HERE)
 

@@ -65,7 +65,7 @@ def test_unorm8_reciprocal_identity():
 # ---- TIFF ----
 def test_tiff_reader_matches_real_libtiff_golden(xb):
     z = np.load(os.path.join(GOLD, "tiff_golden.npz"))
-    assert len(z.files) == 6
+    assert len(z.files) == 6 + 15  # Pillow-written files + one hand-written file per sample layout
     for name in z.files:
         mine = xb.Grid.load_tiff(os.path.join(GOLD, name)).data
         assert np.array_equal(mine, z[name]), name  # bottom-up rows, premultiplied unassociated alpha

@@ -78,6 +78,7 @@ _PROTOTYPES = {
     "xn_ctx_device": (C.c_int, [C.c_void_p]),
     "xn_upload_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "xn_upload_svo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "xn_upload_grid_tiff": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "xn_upload_grid_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "xn_upload_svo_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "xn_convert_resident_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -323,6 +324,13 @@ class Context:
         nx, ny, nz = grid.dimensions
         _check(lib().xn_upload_grid(self._h, grid.data.ctypes.data, nx, ny, nz))
         self.model_dim = (nx, ny, nz)
+
+    def upload_grid_tiff(self, path: str) -> float:
+        """Pipelined TIFF ingest (pinned staging, decode on the device); returns the wall seconds."""
+        dims, secs = (C.c_uint64 * 3)(), C.c_double()
+        _check(lib().xn_upload_grid_tiff(self._h, os.fsencode(path), dims, C.byref(secs)))
+        self.model_dim = tuple(int(d) for d in dims)
+        return secs.value
 
     def upload_grid_device(self, device_ptr: int, nx: int, ny: int, nz: int):
         _check(lib().xn_upload_grid_device(self._h, device_ptr, nx, ny, nz))

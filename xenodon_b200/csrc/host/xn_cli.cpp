@@ -516,9 +516,9 @@ void main_loop(const RenderOptions& o, Devices& devs, const std::string& out_pat
         const uint64_t voxels = dims[0] * dims[1] * dims[2];
         std::printf("%llux%llux%llu = %llu pixels\n", (unsigned long long)dims[0], (unsigned long long)dims[1],
                     (unsigned long long)dims[2], (unsigned long long)voxels);
-        std::vector<uint8_t> grid(voxels * 4);
-        check(xn_tiff_read(o.volume_path.c_str(), grid.data(), grid.size()));
-        for (auto& d : devs.v) check(xn_upload_grid(d.ctx, grid.data(), dims[0], dims[1], dims[2]));
+        // pipelined ingest per device: slices go from the file through page-locked staging to the
+        // device, which decodes them (the volume is replicated; later devices read the page cache)
+        for (auto& d : devs.v) check(xn_upload_grid_tiff(d.ctx, o.volume_path.c_str(), nullptr, nullptr));
         for (int i = 0; i < 3; ++i) model_dim[i] = (uint32_t)dims[i];
     } else {
         uint64_t side = 0, count = 0;

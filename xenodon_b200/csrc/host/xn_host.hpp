@@ -33,6 +33,27 @@ TiffInfo tiff_info(const std::string& path);
 // Grid::load_tiff (src/model/Grid.cpp:27-79) without libtiff; `out` must hold 4*nx*ny*nz bytes
 void tiff_read(const std::string& path, uint8_t* out, uint64_t cap_bytes);
 Grid load_tiff(const std::string& path);
+// Streaming ingest (volume upload pipeline): where the raw sample bytes of each z slice lie in
+// the file and how they decode, so that slices can be read straight into page-locked staging
+// memory and decoded (sample expansion, alpha pre-multiplication, row flip) on the device.
+struct TiffSliceFormat { // identical for every slice of a plan that is `streamable`
+    uint32_t samples;        // 1..4 bytes per pixel
+    uint32_t photometric;    // 0 = white-is-zero, 1 = black-is-zero, 2 = RGB
+    uint32_t has_alpha, unassociated;
+    uint32_t flip;           // file row r is grid row H - 1 - r
+};
+struct TiffRun { // `bytes` contiguous file bytes at `offset`: whole rows in file order
+    uint64_t offset, bytes;
+};
+struct TiffPlan {
+    TiffInfo info{};
+    bool streamable = false; // uncompressed chunky 8-bit strips with one format throughout
+    TiffSliceFormat format{};
+    std::vector<std::vector<TiffRun>> slices; // per z: runs covering nx*ny*samples bytes
+};
+TiffPlan tiff_plan(const std::string& path);
+// host decode of one slice (any supported layout) into out[nx*ny*4], the fallback of the pipeline
+void tiff_read_slice(const std::string& path, uint64_t z, uint8_t* out);
 void tiff_write(const std::string& path, const uint8_t* rgba, uint64_t nx, uint64_t ny, uint64_t nz, bool bigtiff);
 
 // ---- Octree (src/model/Octree.h, Octree.cpp:50-114) ----

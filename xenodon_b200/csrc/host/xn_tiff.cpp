@@ -210,6 +210,22 @@ TiffInfo check_dims(const std::vector<Directory>& dirs) {
     return TiffInfo{width, height, depth};
 }
 
+// Which sample is alpha and whether colours get pre-multiplied, as libtiff's TIFFRGBAImage decides
+// (tif_getimage.c, TIFFRGBAImageBegin + PickContigCase; pinned against libtiff 4.7 in the tests):
+//   RGB : a 4th sample is alpha; unassociated (ExtraSamples = 2) is pre-multiplied, associated or
+//         unspecified is taken as it is;
+//   grey: only a 2-sample image whose ExtraSamples says associated (1) or unassociated (2) has alpha,
+//         and its grey value is never pre-multiplied (putagreytile); anything else is opaque.
+void alpha_rules(const Directory& d, bool& has_alpha, bool& unassociated) {
+    if (d.photometric == 2) {
+        has_alpha = d.samples > 3;
+        unassociated = has_alpha && d.extra_sample == 2;
+    } else {
+        has_alpha = d.samples == 2 && (d.extra_sample == 1 || d.extra_sample == 2);
+        unassociated = false;
+    }
+}
+
 void decode_directory(Reader& r, const Directory& d, uint8_t* out /* W*H*4, grid row order */) {
     if (d.compression != 1) throw Error(XN_ERR_FORMAT, "TIFF: only uncompressed data is supported");
     if (d.bits != 8) throw Error(XN_ERR_FORMAT, "TIFF: only 8 bits per sample are supported");
@@ -220,9 +236,8 @@ void decode_directory(Reader& r, const Directory& d, uint8_t* out /* W*H*4, grid
     const bool rgb = d.photometric == 2;
     if (rgb && spp < 3) throw Error(XN_ERR_FORMAT, "TIFF: RGB image with fewer than 3 samples");
     const uint64_t colour_samples = rgb ? 3 : 1;
-    const bool has_alpha = spp > colour_samples;
-    // tif_getimage.c: unspecified extra sample with > 3 samples is treated as associated alpha
-    const bool unassociated = has_alpha && d.extra_sample == 2;
+    bool has_alpha, unassociated;
+    alpha_rules(d, has_alpha, unassociated);
     const bool flip = d.orientation != 4; // bottom-left files are already in raster order
 
     auto put = [&](uint64_t x, uint64_t file_row, const uint8_t* px) {
@@ -300,6 +315,66 @@ void tiff_read(const std::string& path, uint8_t* out, uint64_t cap_bytes) {
     const uint64_t layer = info.nx * info.ny * 4;
     if (cap_bytes < layer * info.nz) throw Error(XN_ERR_INVALID, "tiff_read: output buffer too small");
     for (uint64_t z = 0; z < info.nz; ++z) decode_directory(r, dirs[z], out + z * layer);
+}
+
+TiffPlan tiff_plan(const std::string& path) {
+    File file(path, "rb");
+    if (!file.f) throw Error(XN_ERR_IO, "Failed to open");
+    uint64_t first;
+    Reader r = open_reader(file.f, first);
+    const auto dirs = read_directories(r, first);
+    TiffPlan plan;
+    plan.info = check_dims(dirs);
+    plan.streamable = true;
+    plan.slices.resize(plan.info.nz);
+    for (uint64_t z = 0; z < plan.info.nz && plan.streamable; ++z) {
+        const Directory& d = dirs[z];
+        const bool rgb = d.photometric == 2;
+        if (d.compression != 1 || d.bits != 8 || d.tiled || d.samples < 1 || d.samples > 4 || d.photometric > 2 ||
+            (d.planar != 1 && d.samples > 1) || (rgb && d.samples < 3)) {
+            plan.streamable = false; // the host decoder reports what is unsupported, or handles tiles
+            break;
+        }
+        TiffSliceFormat f{};
+        f.samples = (uint32_t)d.samples;
+        f.photometric = (uint32_t)d.photometric;
+        bool has_alpha, unassociated;
+        alpha_rules(d, has_alpha, unassociated);
+        f.has_alpha = has_alpha;
+        f.unassociated = unassociated;
+        f.flip = d.orientation != 4;
+        if (z == 0) plan.format = f;
+        else if (std::memcmp(&f, &plan.format, sizeof f) != 0) plan.streamable = false;
+        const uint64_t W = d.width, H = d.height;
+        const uint64_t rps = d.rows_per_strip < H ? d.rows_per_strip : H;
+        if (rps == 0) { plan.streamable = false; break; }
+        const uint64_t nstrips = (H + rps - 1) / rps;
+        if (d.offsets.size() < nstrips) { plan.streamable = false; break; }
+        auto& runs = plan.slices[z];
+        for (uint64_t s = 0; s < nstrips; ++s) {
+            const uint64_t row0 = s * rps, rows = (row0 + rps <= H) ? rps : H - row0;
+            const uint64_t bytes = rows * W * d.samples;
+            if (!d.byte_counts.empty() && s < d.byte_counts.size() && d.byte_counts[s] < bytes) {
+                plan.streamable = false;
+                break;
+            }
+            if (!runs.empty() && runs.back().offset + runs.back().bytes == d.offsets[s]) runs.back().bytes += bytes;
+            else runs.push_back(TiffRun{d.offsets[s], bytes});
+        }
+    }
+    if (!plan.streamable) plan.slices.clear();
+    return plan;
+}
+
+void tiff_read_slice(const std::string& path, uint64_t z, uint8_t* out) {
+    File file(path, "rb");
+    if (!file.f) throw Error(XN_ERR_IO, "Failed to open");
+    uint64_t first;
+    Reader r = open_reader(file.f, first);
+    const auto dirs = read_directories(r, first);
+    check_dims(dirs);
+    if (z >= dirs.size()) throw Error(XN_ERR_INVALID, "tiff_read_slice: no such layer");
+    decode_directory(r, dirs[z], out);
 }
 
 Grid load_tiff(const std::string& path) {

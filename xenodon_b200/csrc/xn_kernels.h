@@ -16,6 +16,12 @@ cudaError_t launch_brick_grid(const uint32_t* linear, uint32_t* bricked, const B
                               uint32_t nz, cudaStream_t stream);
 cudaError_t launch_unbrick_grid(const uint32_t* bricked, uint32_t* linear, const BrickLayout& L, uint32_t nx,
                                 uint32_t ny, uint32_t nz, cudaStream_t stream);
+// raw TIFF samples of one slice -> RGBA8 grid slice (fields as xn::TiffSliceFormat)
+struct TiffDecode {
+    uint32_t samples, photometric, has_alpha, unassociated, flip;
+};
+cudaError_t launch_tiff_decode(const uint8_t* raw, uint32_t* slice, uint32_t W, uint32_t H, const TiffDecode& f,
+                               cudaStream_t stream);
 cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t stream);
 cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride, unsigned long long* out,
                                cudaStream_t stream);

@@ -1,4 +1,5 @@
 // xn_util_kernels.cu -- volume re-layout, synthetic-volume and statistics kernels (sm_100a).
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "xn_brick.h"
@@ -170,6 +171,51 @@ cudaError_t launch_brick_grid(const uint32_t* linear, uint32_t* bricked, const B
 cudaError_t launch_unbrick_grid(const uint32_t* bricked, uint32_t* linear, const BrickLayout& L, uint32_t nx,
                                 uint32_t ny, uint32_t nz, cudaStream_t stream) {
     unbrick_grid_kernel<<<148 * 16, 256, 0, stream>>>(bricked, linear, L, nx, ny, nz);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// volume ingest: raw TIFF sample bytes of one z slice (rows in file order) -> RGBA8 voxels of
+// the grid slice.  What TIFFReadRGBAImage does on the host in the reference
+// (src/model/Grid.cpp:60-75): grey / RGB expansion, white-is-zero inversion, pre-multiplication
+// of unassociated alpha ((c * a + 127) / 255), bottom-up raster order.  One thread per pixel.
+// ---------------------------------------------------------------------------------
+__global__ void tiff_decode_kernel(const uint8_t* __restrict__ raw, uint32_t* __restrict__ slice, uint32_t W, uint32_t H,
+                                   TiffDecode f) {
+    const uint64_t n = (uint64_t)W * H;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = (uint32_t)(i % W), row = (uint32_t)(i / W);
+        uint32_t r, g, b, a = 255u;
+        if (f.samples == 4u && f.photometric == 2u) {
+            const uint32_t v = reinterpret_cast<const uint32_t*>(raw)[i]; // staging is 256-byte aligned
+            r = v & 0xFFu, g = (v >> 8) & 0xFFu, b = (v >> 16) & 0xFFu, a = v >> 24;
+        } else {
+            const uint8_t* px = raw + i * f.samples;
+            uint32_t cs;
+            if (f.photometric == 2u) {
+                r = px[0], g = px[1], b = px[2];
+                cs = 3;
+            } else {
+                r = g = b = f.photometric == 0u ? 255u - px[0] : px[0];
+                cs = 1;
+            }
+            if (f.has_alpha) a = px[cs];
+        }
+        if (f.unassociated) {
+            r = (r * a + 127u) / 255u;
+            g = (g * a + 127u) / 255u;
+            b = (b * a + 127u) / 255u;
+        }
+        const uint32_t y = f.flip ? H - 1u - row : row;
+        slice[(uint64_t)y * W + x] = r | (g << 8) | (b << 16) | (a << 24);
+    }
+}
+
+cudaError_t launch_tiff_decode(const uint8_t* raw, uint32_t* slice, uint32_t W, uint32_t H, const TiffDecode& f,
+                               cudaStream_t stream) {
+    const uint64_t n = (uint64_t)W * H;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+    tiff_decode_kernel<<<blocks, 256, 0, stream>>>(raw, slice, W, H, f);
     return cudaGetLastError();
 }
 

@@ -289,3 +289,47 @@ def test_dda_bricked_gpu_convert_and_auto_policy(xb):
         assert tree.nodes.tobytes() == host_tree.nodes.tobytes()
     finally:
         ctx.close()
+
+
+def _deep_chain_tree(xb, depth, seed=9):
+    """Hand-built octree `depth` levels deep: at every level one child (a different octant each
+    time) is internal, the other seven are coloured leaves; node 0 = root, children by index."""
+    rng = np.random.default_rng(seed)
+    nodes = []
+
+    def leaf(d):
+        n = np.zeros((), dtype=xb.NODE_DTYPE)
+        n["color"] = int(rng.integers(0, 1 << 24)) | 0xFF000000
+        n["is_leaf_depth"] = 0x80000000 | d
+        nodes.append(n)
+        return len(nodes) - 1
+
+    nodes.append(np.zeros((), dtype=xb.NODE_DTYPE))  # root
+    cur = 0
+    for d in range(depth):
+        nodes[cur]["is_leaf_depth"] = d
+        nodes[cur]["color"] = 0xFF808080
+        deeper = int(rng.integers(0, 8)) if d + 1 < depth else -1
+        nxt = None
+        for c in range(8):
+            if c == deeper:
+                nodes.append(np.zeros((), dtype=xb.NODE_DTYPE))
+                nxt = len(nodes) - 1
+                nodes[cur]["children"][c] = nxt
+            else:
+                nodes[cur]["children"][c] = leaf(d + 1)
+        cur = nxt
+    return xb.Octree(np.array(nodes, dtype=xb.NODE_DTYPE), 1 << depth)
+
+
+@pytest.mark.parametrize("traversal", SVO_TRAVERSALS)
+@pytest.mark.parametrize("depth", [13, 20])
+def test_deep_trees_use_the_deep_stack_instantiation(xb, xo, traversal, depth):
+    """Trees deeper than 12 levels run the 32-level (esvo) / 24-level (svo_df) stack instantiations;
+    a chain of single internal children reaches those depths with a few hundred nodes."""
+    tree = _deep_chain_tree(xb, depth)
+    if traversal == "svo-rope":
+        tree = xb.Octree(xo.generate_ropes(tree.nodes, tree.side), tree.side)
+    for cam in ("orbit", "inside"):
+        _compare(xb, xo, traversal, tree=tree, camera=CAMERAS[cam], output=(0, 0, 96, 54), display=(0, 0, 96, 54),
+                 emission=1.0)

@@ -352,7 +352,15 @@ void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) 
     XN_CUDA(cudaMalloc(&d_max, sizeof(uint32_t)));
     XN_CUDA(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), ctx->stream));
     XN_CUDA(xn::launch_relayout(d_raw, count, ctx->nodes, d_max, ctx->stream));
-    XN_CUDA(xn::build_compact_nodes(d_raw, count, &ctx->cnodes, &ctx->internal_count, ctx->stream));
+    {
+        const cudaError_t e = xn::build_compact_nodes(d_raw, count, &ctx->cnodes, &ctx->internal_count, ctx->stream);
+        if (e == cudaErrorInvalidValue) {
+            cudaGetLastError();
+            ctx->free_nodes();
+            throw xn::Error(XN_ERR_LIMIT, "octree has more than 2^28 internal nodes");
+        }
+        XN_CUDA(e);
+    }
     uint32_t root[2] = {0, 0};
     XN_CUDA(cudaMemcpyAsync(root, (const uint8_t*)d_raw + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
     uint32_t maxd = 0;

@@ -30,7 +30,8 @@ static_assert(sizeof(DNode) == 64, "device node must be 64 bytes");
 // level), so the upper levels are one contiguous range that an L2 access-policy window keeps
 // resident.  One 32-bit word per child:
 //   leaf child     : bit 31 set | depth << 24 | b << 16 | g << 8 | r   (the same bits as `meta`)
-//   internal child : its compact index (bit 31 clear)
+//   internal child : the word offset of its record = compact index * 8 (bit 31 clear; up to 2^28
+//                    internal nodes, i.e. trees of about 2^31 nodes)
 // A leaf's own node record is never read by these three traversals (everything they need about a
 // leaf is in its parent's word), so leaves -- 7/8 of a tree -- occupy no space here.
 struct __align__(32) CNode {

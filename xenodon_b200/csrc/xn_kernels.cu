@@ -40,9 +40,13 @@
 #ifndef XN_DDA_SEGMENTS
 #define XN_DDA_SEGMENTS 1
 #endif
+// ESVO PUSH: 1 = always write the stack entry, 0 = only when the child exits before its parent (`h`)
+#ifndef XN_ESVO_ALWAYS_STORE
+#define XN_ESVO_ALWAYS_STORE 1
+#endif
 // ESVO POP: 1 = differing bits from the old/new positions and mask-based truncation
 #ifndef XN_ESVO_POP
-#define XN_ESVO_POP 0
+#define XN_ESVO_POP 1
 #endif
 
 namespace xn {
@@ -641,8 +645,10 @@ __device__ __forceinline__ uint2 load_slot(const DNode* __restrict__ nodes, uint
     return __ldg(&nodes[node].slot[child]);
 }
 // compact residency: one word per child (leaf: meta bits, internal: compact child index)
+// `node` is the WORD offset of the record (compact index * 8, as stored in the parent's word), so the
+// address of a child word is one OR and one scaled add
 __device__ __forceinline__ uint32_t load_word(const CNode* __restrict__ nodes, uint32_t node, uint32_t child) {
-    return __ldg(&nodes[node].w[child]);
+    return __ldg(reinterpret_cast<const uint32_t*>(nodes) + (node | child));
 }
 __device__ __forceinline__ bool word_is_leaf(uint32_t w) { return (int32_t)w < 0; }
 // child descriptor as (index, meta) from either residency
@@ -823,13 +829,34 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
 // `if (c) { pos += d; idx ^= bit; }` into compare + FADD + FSEL + SEL chains on the ALU pipe,
 // which bounds this kernel (ncu: ALU 70 %, issue 72 %); predicated FADDs run on the FMA pipe.
 #ifndef XN_ESVO_PTX
-#define XN_ESVO_PTX 0
+#define XN_ESVO_PTX 2
 #endif
 // ADVANCE (esvo.comp:96-104): axes whose corner time equals tc_max step back by `se`;
 // returns the step mask (x = 4, y = 2, z = 1)
 __device__ __forceinline__ uint32_t esvo_advance(float tcorx, float tcory, float tcorz, float tc_max, float se,
-                                                 float& posx, float& posy, float& posz) {
-#if XN_ESVO_PTX
+                                                 float& posx, float& posy, float& posz, float& fx, float& fy,
+                                                 float& fz) {
+#if XN_ESVO_PTX == 2
+    // comparison results as 1.0f / 0.0f (one FSET each); the position update and the step mask are
+    // then exact FMAs on the FMA pipe (pos - 1.0 * se, 4 ax + 2 ay + az) and one float -> int
+    // conversion, instead of predicate -> SEL / FSEL chains on the ALU pipe
+    uint32_t m;
+    asm("{\n\t"
+        ".reg .f32 mf;\n\t"
+        "set.le.f32.f32 %4, %7, %10;\n\t"
+        "set.le.f32.f32 %5, %8, %10;\n\t"
+        "set.le.f32.f32 %6, %9, %10;\n\t"
+        "fma.rn.f32 %1, %4, %11, %1;\n\t"
+        "fma.rn.f32 %2, %5, %11, %2;\n\t"
+        "fma.rn.f32 %3, %6, %11, %3;\n\t"
+        "fma.rn.f32 mf, %4, 0f40800000, %6;\n\t"
+        "fma.rn.f32 mf, %5, 0f40000000, mf;\n\t"
+        "cvt.rzi.u32.f32 %0, mf;\n\t"
+        "}"
+        : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz), "=&f"(fx), "=&f"(fy), "=&f"(fz)
+        : "f"(tcorx), "f"(tcory), "f"(tcorz), "f"(tc_max), "f"(-se));
+    return m;
+#elif XN_ESVO_PTX
     uint32_t m;
     asm("{\n\t"
         ".reg .pred ax, ay, az;\n\t"
@@ -847,19 +874,38 @@ __device__ __forceinline__ uint32_t esvo_advance(float tcorx, float tcory, float
         "}"
         : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
         : "f"(tcorx), "f"(tcory), "f"(tcorz), "f"(tc_max), "f"(se));
+    fx = (m & 4u) ? 1.0f : 0.0f, fy = (m & 2u) ? 1.0f : 0.0f, fz = (m & 1u) ? 1.0f : 0.0f;
     return m;
 #else
     const bool ax = tcorx <= tc_max, ay = tcory <= tc_max, az = tcorz <= tc_max;
     if (ax) posx -= se;
     if (ay) posy -= se;
     if (az) posz -= se;
+    fx = ax ? 1.0f : 0.0f, fy = ay ? 1.0f : 0.0f, fz = az ? 1.0f : 0.0f;
     return (ax ? 4u : 0u) | (ay ? 2u : 0u) | (az ? 1u : 0u);
 #endif
 }
 // PUSH child selection (esvo.comp:84-90): the half of the node the ray enters first on every axis
 __device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, float tcenz, float t_min, float se,
                                                      float& posx, float& posy, float& posz) {
-#if XN_ESVO_PTX
+#if XN_ESVO_PTX == 2
+    uint32_t m;
+    asm("{\n\t"
+        ".reg .f32 ax, ay, az, mf;\n\t"
+        "set.gt.f32.f32 ax, %4, %7;\n\t"
+        "set.gt.f32.f32 ay, %5, %7;\n\t"
+        "set.gt.f32.f32 az, %6, %7;\n\t"
+        "fma.rn.f32 %1, ax, %8, %1;\n\t"
+        "fma.rn.f32 %2, ay, %8, %2;\n\t"
+        "fma.rn.f32 %3, az, %8, %3;\n\t"
+        "fma.rn.f32 mf, ax, 0f40800000, az;\n\t"
+        "fma.rn.f32 mf, ay, 0f40000000, mf;\n\t"
+        "cvt.rzi.u32.f32 %0, mf;\n\t"
+        "}"
+        : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
+        : "f"(tcenx), "f"(tceny), "f"(tcenz), "f"(t_min), "f"(se));
+    return m;
+#elif XN_ESVO_PTX
     uint32_t m;
     asm("{\n\t"
         ".reg .pred ax, ay, az;\n\t"
@@ -894,7 +940,11 @@ __device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, f
 // ---------------------------------------------------------------------------------
 template <bool STATS, bool STRICT, int LEVELS>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(const __grid_constant__ FrameParams p) {
-    __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS]; // [level][thread] = (parent, bits(t_max))
+    // [scale][thread] = (parent, bits(t_max)).  Trees this instantiation is launched for are shallower
+    // than LEVELS; the index is clamped instead of bounds-tested, so a malformed file (a cycle of
+    // child pointers) aliases its own thread's last entry and nothing else.  Shared memory is
+    // kept small on purpose: what the stacks take is carved out of the L1 cache.
+    __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS];
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
@@ -923,7 +973,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
 
     float t_min = max_elem(F3(2.0f * tcx - tbx, 2.0f * tcy - tby, 2.0f * tcz - tbz));
     float t_max = min_elem(F3(tcx - tbx, tcy - tby, tcz - tbz));
+#if !XN_ESVO_ALWAYS_STORE
     float h = t_max;
+#endif
     t_min = gmax(t_min, 0.0f);
     t_max = gmin(t_max, sqrtf(3.0f));
 
@@ -936,7 +988,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
     if (1.5f * tcz - tbz > t_min) { posz = 1.5f; idx ^= 1u; }
 
     Accum<STRICT> acc;
-    const uint32_t stack = stack_base(stack_mem);
+    // entries are indexed by `scale` itself, as in esvo.comp:34-35: the base is moved down by the
+    // (23 - LEVELS) scales this instantiation never reaches, so a push / pop address is one scaled add
+    constexpr uint32_t MIN_SCALE = LEVELS >= 23 ? 0u : 23u - (uint32_t)LEVELS;
+    const uint32_t stack = stack_base(stack_mem) - MIN_SCALE * (uint32_t)(BLOCK_THREADS * sizeof(uint2));
     const CNode* __restrict__ nodes = p.cnodes;
 
     // The child descriptor of (parent, idx) is requested at the END of the previous iteration,
@@ -960,12 +1015,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
                     st.read(4); // color
                     acc.add(s, tv_max - t_min);
                 } else {
-                    // PUSH
-                    if (tc_max < h) {
-                        const uint32_t level = (cast_stack_depth - 1u) - scale;
-                        if (level < (uint32_t)LEVELS) stack_store(stack, level, parent, __float_as_uint(t_max));
-                    }
+                    // PUSH.  esvo.comp:79-82 skips the stack write when the child's exit time is not
+                    // below `h` (the parent will never be popped to); writing always stores the
+                    // same (parent, t_max) the reference would have stored at this level, is never
+                    // observable, and saves the comparison and the bookkeeping of h.
+#if XN_ESVO_ALWAYS_STORE
+                    stack_store(stack, max(scale, MIN_SCALE), parent,
+                                __float_as_uint(t_max));
+#else
+                    if (tc_max < h)
+                        stack_store(stack, max(scale, MIN_SCALE), parent,
+                                    __float_as_uint(t_max));
                     h = tc_max;
+#endif
                     parent = s;
                     --scale;
                     scale_exp2 *= 0.5f;
@@ -980,10 +1042,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
 
         if (!pushed) {
             // ADVANCE
-#if XN_ESVO_POP
-            const float ox = posx, oy = posy, oz = posz;
-#endif
-            const uint32_t step_mask = esvo_advance(tcorx, tcory, tcorz, tc_max, scale_exp2, posx, posy, posz);
+            float fx, fy, fz; // 1.0 on the axes that stepped
+            const uint32_t step_mask = esvo_advance(tcorx, tcory, tcorz, tc_max, scale_exp2, posx, posy, posz, fx, fy, fz);
             const bool ax = (step_mask & 4u) != 0u, ay = (step_mask & 2u) != 0u, az = (step_mask & 1u) != 0u;
             t_min = tc_max;
             idx ^= step_mask;
@@ -993,6 +1053,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
 #if XN_ESVO_POP
                 // pos + scale_exp2 is the position before the step, exactly; axes that did not
                 // step contribute 0 (esvo.comp:108-116)
+                const float ox = __fmaf_rn(fx, scale_exp2, posx), oy = __fmaf_rn(fy, scale_exp2, posy),
+                            oz = __fmaf_rn(fz, scale_exp2, posz);
                 const uint32_t dbits = (__float_as_uint(ox) ^ __float_as_uint(posx)) |
                                        (__float_as_uint(oy) ^ __float_as_uint(posy)) |
                                        (__float_as_uint(oz) ^ __float_as_uint(posz));
@@ -1008,9 +1070,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
                 scale = 31u - (uint32_t)__clz((int)dbits);
                 if (scale >= cast_stack_depth) break; // left the cube (also guards the reference's
                                                       // underflowed stack read, esvo.comp:119-123)
-                scale_exp2 = __uint_as_float((scale - cast_stack_depth + 127u) << 23);
-                const uint32_t level = (cast_stack_depth - 1u) - scale;
-                const uint2 e = level < (uint32_t)LEVELS ? stack_load(stack, level) : make_uint2(0u, 0u);
+                scale_exp2 = __uint_as_float(scale * 0x00800000u + 0x34000000u); // exp2(scale - 23): one IMAD
+                const uint2 e = stack_load(stack, max(scale, MIN_SCALE));
+#if !XN_ESVO_ALWAYS_STORE
+                h = 0.0f;
+#endif
                 parent = e.x;
                 t_max = __uint_as_float(e.y);
                 const uint32_t shx = __float_as_uint(posx) >> scale, shy = __float_as_uint(posy) >> scale,
@@ -1026,7 +1090,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) esvo_kernel(
                 posz = __uint_as_float(shz << scale);
 #endif
                 idx = (shx & 1u) * 4u + (shy & 1u) * 2u + (shz & 1u);
-                h = 0.0f;
             }
         }
         s = load_word(nodes, parent, idx ^ octant_mask);

@@ -84,7 +84,7 @@ __global__ void compact_emit_kernel(const uint32_t* __restrict__ raw, uint64_t c
         uint32_t child = n[c];
         if (child >= count) child = 0; // malformed file: never index out of bounds
         const uint32_t* cn = raw + (uint64_t)child * 10u;
-        w[c] = (cn[9] & 0x80000000u) ? make_meta(cn[8], cn[9]) : rank[child];
+        w[c] = (cn[9] & 0x80000000u) ? make_meta(cn[8], cn[9]) : rank[child] << 3; // word offset of the record
     }
     uint4* o = reinterpret_cast<uint4*>(out + j);
     o[0] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -124,6 +124,7 @@ cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, 
     unsigned long long n_internal = 0;
     XN_TRY(cudaMemcpyAsync(&n_internal, d_n, 8, cudaMemcpyDeviceToHost, stream));
     XN_TRY(cudaStreamSynchronize(stream));
+    if (n_internal > (1ull << 28)) return done(cudaErrorInvalidValue); // word offsets must fit 31 bits
     XN_TRY(cudaMalloc(&nodes, n_internal * sizeof(CNode)));
     const unsigned iblocks = (unsigned)((n_internal + threads - 1) / threads);
     compact_rank_kernel<<<iblocks, threads, 0, stream>>>(v_out, n_internal, rank);

@@ -436,6 +436,8 @@ def main():
     achieved = alg_bytes_per_frame / (mean_kernel_ms / 1e3) / 1e9
     kernel_name = {"dda": "dda_kernel", "esvo": "esvo_kernel", "svo-rope": "svo_rope_kernel",
                    "svo-df": "svo_df_kernel", "svo-naive": "svo_naive_kernel"}[traversal]
+    if traversal == "dda" and ctx.grid_layout()[0] == xb.LAYOUT_TEXTURE:
+        kernel_name = "dda_tex_kernel"
     result = {
         "metric": "Mrays/s", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": n_gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": round(region_all / steps, 5), "higher_is_better": True,
@@ -457,7 +459,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 1), "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": measured_traffic(args.workload, kernel_name) if n_gpus == 1 else None,
-                     "traffic_source": "profiles/traffic.json (ncu --set full capture of camera frame 3)",
+                     "traffic_source": "profiles/traffic.json (ncu --set full capture of one camera frame)",
                      "algorithmic_bytes_per_launch": round(alg_bytes_per_frame),
                      "steps_per_launch": round(alg_steps_per_frame),
                      "mean_kernel_ms": round(mean_kernel_ms, 5),

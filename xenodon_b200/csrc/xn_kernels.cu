@@ -40,6 +40,10 @@
 #ifndef XN_DDA_SEGMENTS
 #define XN_DDA_SEGMENTS 1
 #endif
+// octree descent (svo_naive / svo_rope): child selection with comparison flags and FMAs
+#ifndef XN_DESCEND_FLAGS
+#define XN_DESCEND_FLAGS 1
+#endif
 // ESVO PUSH: 1 = always write the stack entry, 0 = only when the child exits before its parent (`h`)
 #ifndef XN_ESVO_ALWAYS_STORE
 #define XN_ESVO_ALWAYS_STORE 1
@@ -680,6 +684,28 @@ __device__ __forceinline__ void descend(const NODE* __restrict__ nodes, f3 pos, 
         st.read(4); // is_leaf_depth
         if (meta_is_leaf(meta)) return;
         extent *= 0.5f;
+#if XN_DESCEND_FLAGS
+        // comparison results as 1.0 / 0.0 (FSET), then exact FMAs: offset += mask * extent is what
+        // the shader writes (svo_naive.comp:21-23), and the child index is 4 mx + 2 my + mz
+        uint32_t child;
+        {
+            const float cx = offset.x + extent, cy = offset.y + extent, cz = offset.z + extent;
+            asm("{\n\t"
+                ".reg .f32 fx, fy, fz, mf;\n\t"
+                "set.ge.f32.f32 fx, %4, %7;\n\t"
+                "set.ge.f32.f32 fy, %5, %8;\n\t"
+                "set.ge.f32.f32 fz, %6, %9;\n\t"
+                "fma.rn.f32 %1, fx, %10, %1;\n\t"
+                "fma.rn.f32 %2, fy, %10, %2;\n\t"
+                "fma.rn.f32 %3, fz, %10, %3;\n\t"
+                "fma.rn.f32 mf, fx, 0f40800000, fz;\n\t"
+                "fma.rn.f32 mf, fy, 0f40000000, mf;\n\t"
+                "cvt.rzi.u32.f32 %0, mf;\n\t"
+                "}"
+                : "=r"(child), "+f"(offset.x), "+f"(offset.y), "+f"(offset.z)
+                : "f"(pos.x), "f"(pos.y), "f"(pos.z), "f"(cx), "f"(cy), "f"(cz), "f"(extent));
+        }
+#else
         const bool mx = pos.x >= offset.x + extent;
         const bool my = pos.y >= offset.y + extent;
         const bool mz = pos.z >= offset.z + extent;
@@ -688,6 +714,7 @@ __device__ __forceinline__ void descend(const NODE* __restrict__ nodes, f3 pos, 
         if (mx) offset.x += extent;
         if (my) offset.y += extent;
         if (mz) offset.z += extent;
+#endif
         st.read(4); // children[child]
         const uint2 s = load_child(nodes, node, child);
         node = s.x;

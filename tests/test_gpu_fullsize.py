@@ -111,3 +111,71 @@ def test_tile_seams_at_full_size(xb, scene):
         ctx.sync()
         assert np.array_equal(ctx.download(), full[y:y + h, x:x + w])
     ctx.set_target((0, 0, W, H))
+
+
+@pytest.mark.parametrize("dims,big", [((1024, 1024, 1024), False), ((2048, 2048, 600), True)])
+def test_grid_residency_layouts_agree_at_large_sizes(xb, dims, big):
+    """2^30 voxels (the size AUTO moves to the texture residency) and 2.5 * 2^30 voxels (64-bit
+    indexing: GridCursor<true>, BrickCursor<true>): the same frames from the linear, bricked and
+    texture residencies must be identical in the strict mode, within 1/255 in the fast mode, with
+    identical per-frame step totals; the octree traversals of the lossless tree of the same volume
+    must agree with each other across the two octree residencies."""
+    from xenodon_b200 import cameras
+    cams = cameras.camera_benchmark()
+    w, h = 1280, 720
+    ctx = xb.Context(0)
+    try:
+        ctx.synth_grid(xb.SYNTH_TNG, *dims)
+        assert ctx.grid_layout()[0] == xb.LAYOUT_TEXTURE  # AUTO at these sizes
+        ctx.set_target((0, 0, w, h))
+        ctx.set_params((1, 1, 1), dims, 4.0)
+        frames = [cams[10], cams[120]]
+        out = {}
+        for layout in (xb.LAYOUT_TEXTURE, xb.LAYOUT_LINEAR, xb.LAYOUT_BRICKED):
+            ctx.set_grid_layout(layout)
+            have, nbytes = ctx.grid_layout()
+            assert have == layout and nbytes >= 4 * dims[0] * dims[1] * dims[2]
+            for strict in (True, False):
+                ctx.set_precision(strict)
+                for i, f in enumerate(frames):
+                    cam = _cam(f)
+                    ctx.render("dda", cam)
+                    ctx.sync()
+                    img = ctx.download()
+                    totals = ctx.stats_pass("dda", cam, per_ray=False)[2]
+                    out[(layout, strict, i)] = (img, totals)
+        for strict in (True, False):
+            for i in range(len(frames)):
+                ref_img, ref_tot = out[(xb.LAYOUT_LINEAR, strict, i)]
+                assert ref_img[..., :3].any()
+                for layout in (xb.LAYOUT_TEXTURE, xb.LAYOUT_BRICKED):
+                    img, tot = out[(layout, strict, i)]
+                    assert tot == ref_tot, (layout, strict, i)
+                    d = np.abs(img.astype(int) - ref_img.astype(int)).max()
+                    assert d == 0 if (strict or layout == xb.LAYOUT_BRICKED) else d <= 1, (layout, strict, i, d)
+        if not big:
+            # Lossless octree of the same volume (135 M nodes, depth 10), built on the GPU.  esvo and
+            # svo_naive read the compact level-order residency, svo_rope the 64-byte file-order
+            # records -- two residencies built by independent code -- so their agreement checks both
+            # at a size the oracle cannot reach.  DDA vs ESVO is only a sanity bound: the reference's
+            # DDA drops the first voxel of rays that enter through a far face (ivec3(ro) = n is out of
+            # range, dda.comp:24-38), so silhouette pixels legitimately differ.
+            ctx.set_grid_layout(xb.LAYOUT_AUTO)
+            _, stats, count, side = ctx.convert_resident_grid(chan_diff=0, type=xb.TYPE_ROPE, bind=True)
+            assert side == dims[0] and count > 100_000_000 and stats["depth"] == 10
+            ctx.set_precision(True)
+            ctx.set_params((1, 1, 1), (side,) * 3, 4.0)
+            for i, f in enumerate(frames):
+                cam = _cam(f)
+                imgs = {}
+                for t in ("esvo", "svo-rope", "svo-naive"):
+                    ctx.render(t, cam)
+                    ctx.sync()
+                    imgs[t] = ctx.download().astype(int)
+                for t in ("svo-rope", "svo-naive"):
+                    d = np.abs(imgs[t] - imgs["esvo"]).max(axis=-1)
+                    assert (d <= 1).mean() >= 0.999, (t, i, float((d <= 1).mean()), int(d.max()))
+                d = np.abs(imgs["esvo"] - out[(xb.LAYOUT_LINEAR, True, i)][0].astype(int)).max(axis=-1)
+                assert (d <= 1).mean() >= 0.95, (i, float((d <= 1).mean()))
+    finally:
+        ctx.close()

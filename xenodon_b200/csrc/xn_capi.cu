@@ -344,6 +344,41 @@ void apply_layout(xn_ctx* ctx) {
     }
 }
 
+// L2 access-policy window over the head of the compact node array.  The records are in level
+// order, so the head IS the upper levels of the tree, which every ray walks: marking them
+// persisting keeps the streaming lower levels (and the frame stores) from evicting them.
+// XN_L2_WINDOW_MB: size of the window (default 0 = off: measured without effect, profiles/README.md); the device's persisting-L2 limit
+// is raised to match.  Trees that fit in the window entirely gain nothing (they live in L2 anyway).
+void apply_l2_window(xn_ctx* ctx) {
+    uint64_t window_mb = 0;
+    if (const char* e = std::getenv("XN_L2_WINDOW_MB")) window_mb = std::strtoull(e, nullptr, 10);
+    cudaStreamAttrValue attr{};
+    const uint64_t bytes = ctx->internal_count * sizeof(xn::CNode);
+    if (window_mb == 0 || !ctx->cnodes || bytes <= (window_mb << 20)) {
+        attr.accessPolicyWindow.num_bytes = 0; // no window
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+        return;
+    }
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    uint64_t want = window_mb << 20;
+    want = std::min<uint64_t>(want, (uint64_t)std::max(max_persist, 0));
+    want = std::min<uint64_t>(want, (uint64_t)std::max(max_window, 0));
+    if (want == 0) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    attr.accessPolicyWindow.base_ptr = ctx->cnodes;
+    attr.accessPolicyWindow.num_bytes = want;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) {
     // d_raw: count 40-byte nodes on the device; produce the 64-byte resident layout
     ctx->free_nodes();
@@ -371,6 +406,7 @@ void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) 
         ctx->free_nodes();
         throw xn::Error(XN_ERR_LIMIT, "octree deeper than 23 levels (the traversal stack depth of the reference)");
     }
+    apply_l2_window(ctx);
     ctx->root_meta = xn::make_meta(root[0], root[1]);
     ctx->max_depth = maxd;
     ctx->node_count = count;

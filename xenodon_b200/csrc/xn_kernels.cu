@@ -300,6 +300,64 @@ __device__ __forceinline__ void dda_step<GridCursor<false>>(GridCursor<false>& c
         : "+f"(sdx), "+f"(sdy), "+f"(sdz), "+r"(cur.idx), "+f"(t), "=f"(dt)
         : "f"(tdx), "f"(tdy), "f"(tdz), "r"(cur.dix), "r"(cur.diy), "r"(cur.diz));
 }
+// the same for the bricked cursors: t = d + K is unconditional, the mask is applied under the
+// predicate (d = t & mask), so an axis step is one IADD and one predicated LOP3
+template <>
+__device__ __forceinline__ void dda_step<BrickCursor<false>>(BrickCursor<false>& cur, float& sdx, float& sdy,
+                                                             float& sdz, float tdx, float tdy, float tdz, float& t,
+                                                             float& dt) {
+    asm("{\n\t"
+        ".reg .pred px, py, pz;\n\t"
+        ".reg .f32 t0;\n\t"
+        ".reg .b32 ux, uy, uz;\n\t"
+        "min.f32 t0, %1, %2;\n\t"
+        "min.f32 t0, %0, t0;\n\t"
+        "setp.eq.f32 px, %0, t0;\n\t"
+        "setp.eq.f32 py, %1, t0;\n\t"
+        "setp.eq.f32 pz, %2, t0;\n\t"
+        "sub.f32 %7, t0, %6;\n\t"
+        "mov.f32 %6, t0;\n\t"
+        "add.u32 ux, %3, %11;\n\t"
+        "add.u32 uy, %4, %12;\n\t"
+        "add.u32 uz, %5, %13;\n\t"
+        "@px add.f32 %0, %0, %8;\n\t"
+        "@py add.f32 %1, %1, %9;\n\t"
+        "@pz add.f32 %2, %2, %10;\n\t"
+        "@px and.b32 %3, ux, %14;\n\t"
+        "@py and.b32 %4, uy, %15;\n\t"
+        "@pz and.b32 %5, uz, %16;\n\t"
+        "}"
+        : "+f"(sdx), "+f"(sdy), "+f"(sdz), "+r"(cur.dx), "+r"(cur.dy), "+r"(cur.dz), "+f"(t), "=f"(dt)
+        : "f"(tdx), "f"(tdy), "f"(tdz), "r"(cur.kx), "r"(cur.ky), "r"(cur.kz), "r"(cur.mx), "r"(cur.my), "r"(cur.mz));
+}
+template <>
+__device__ __forceinline__ void dda_step<BrickCursor<true>>(BrickCursor<true>& cur, float& sdx, float& sdy, float& sdz,
+                                                            float tdx, float tdy, float tdz, float& t, float& dt) {
+    asm("{\n\t"
+        ".reg .pred px, py, pz;\n\t"
+        ".reg .f32 t0;\n\t"
+        ".reg .b32 ux, uy;\n\t"
+        ".reg .b64 uz;\n\t"
+        "min.f32 t0, %1, %2;\n\t"
+        "min.f32 t0, %0, t0;\n\t"
+        "setp.eq.f32 px, %0, t0;\n\t"
+        "setp.eq.f32 py, %1, t0;\n\t"
+        "setp.eq.f32 pz, %2, t0;\n\t"
+        "sub.f32 %7, t0, %6;\n\t"
+        "mov.f32 %6, t0;\n\t"
+        "add.u32 ux, %3, %11;\n\t"
+        "add.u32 uy, %4, %12;\n\t"
+        "add.u64 uz, %5, %13;\n\t"
+        "@px add.f32 %0, %0, %8;\n\t"
+        "@py add.f32 %1, %1, %9;\n\t"
+        "@pz add.f32 %2, %2, %10;\n\t"
+        "@px and.b32 %3, ux, %14;\n\t"
+        "@py and.b32 %4, uy, %15;\n\t"
+        "@pz and.b64 %5, uz, %16;\n\t"
+        "}"
+        : "+f"(sdx), "+f"(sdy), "+f"(sdz), "+r"(cur.dx), "+r"(cur.dy), "+l"(cur.dz), "+f"(t), "=f"(dt)
+        : "f"(tdx), "f"(tdy), "f"(tdz), "r"(cur.kx), "r"(cur.ky), "l"(cur.kz), "r"(cur.mx), "r"(cur.my), "l"(cur.mz));
+}
 #endif
 
 // ---------------------------------------------------------------------------------

@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_tex_kernel(const __grid_con
     typedef TexFetch<STRICT> TF;
     typedef typename TF::texel texel;
     uint32_t ix, iy;
-    thread_pixel(p, ix, iy);
+    thread_pixel<true>(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
     RayStats<STATS> st;
 

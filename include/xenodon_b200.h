@@ -130,10 +130,15 @@ XN_API int xn_download_grid(xn_ctx* ctx, uint8_t* rgba_out, uint64_t cap_bytes);
 
 /* Residency layout of the grid in HBM.  The reference hands its grid to the driver as an
  * "optimal tiling" 3-D image (src/render/DdaRaytraceAlgorithm.cpp:16-34); here the order is
- * explicit: x-major linear, or 8x8x8 bricks with Morton order inside (one 32-byte sector = a
- * 2x2x2 voxel cube), which keeps a warp's texels in few sectors whatever the ray direction.
- * AUTO (default) bricks large volumes only.  The mode applies to the grid resident now and to
- * later uploads; images are identical in every layout.  xn_grid_layout reports what is resident
+ * explicit: x-major linear (read with plain loads); 8x8x8 bricks with Morton order inside (one
+ * 32-byte sector = a 2x2x2 voxel cube); or a 3-D CUDA array read through the texture units
+ * (block-linear tiling, border colour 0 = the reference's clamp-to-border sampler), where the
+ * texture unit does the address arithmetic, the bounds test and the byte -> float conversion.
+ * The last two keep a warp's texels in few sectors whatever the ray direction.  AUTO (default)
+ * keeps volumes below 2^29 voxels linear and puts larger ones in the texture residency (measured,
+ * profiles/README.md).  The mode applies to the grid resident now and to later uploads; exactly one
+ * copy is resident at a time.  Strict-mode images and per-ray step counts are identical in every
+ * layout; fast-mode images agree within 1/255.  xn_grid_layout reports what is resident
  * (XN_GRID_LAYOUT_AUTO = no grid) and the bytes it occupies. */
 enum { XN_GRID_LAYOUT_AUTO = 0, XN_GRID_LAYOUT_LINEAR = 1, XN_GRID_LAYOUT_BRICKED = 2, XN_GRID_LAYOUT_TEXTURE = 3 };
 XN_API int xn_set_grid_layout(xn_ctx* ctx, int mode);

@@ -294,7 +294,16 @@ void ensure_linear(xn_ctx* ctx) {
     XN_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+void make_texture_unguarded(xn_ctx* ctx);
 void make_texture(xn_ctx* ctx) {
+    try {
+        make_texture_unguarded(ctx);
+    } catch (...) {
+        ctx->free_texture(); // never leave a half-built residency behind
+        throw;
+    }
+}
+void make_texture_unguarded(xn_ctx* ctx) {
     const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
     XN_CUDA(cudaMalloc3DArray(&ctx->tex_array, &fmt, make_cudaExtent(ctx->nx, ctx->ny, ctx->nz)));
     const cudaMemcpy3DParms cp = array_copy_parms(ctx, true);

@@ -834,13 +834,61 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_naive_ke
 }
 
 // ---------------------------------------------------------------------------------
-// svo_df (resources/svo_df.comp:6-85)
-// Stack entry = (node, child_idx | depth << 3): the depth of the pushed node is kept so
-// the pop does not re-read is_leaf_depth (svo_df.comp:58) from memory.
+// svo_df (resources/svo_df.comp:6-85): exhaustive depth-first visit, children in index order.
+//
+// The shader slab-tests the eight children of a node one loop iteration at a time, rebuilding
+// each child's corner from the previous one with three mod()s.  Here the eight tests of a node
+// are done together when the node is entered: on every axis the children's boxes are bounded by
+// three planes (corner, corner + side, corner + 2 side), whose ray parameters are computed once
+// with exactly the shader's operations -- pos * rrd - bias and (pos + side) * rrd - bias, where
+// pos is the corner or corner + side -- so every child's (t_min, t_max) is the value the shader
+// computes, the hit mask is the shader's `t_min < t_max && t_max > 0`, and only hit children are
+// visited, in index order (the accumulation order of the shader).  A stack entry keeps the
+// children still to visit and is written only when there are any; the corner is restored on a pop
+// by rounding down to the node's size (exact: corners are sums of powers of two).  The instrumented build counts the iterations and reads of
+// the shader's loop: 8 iterations per entered node, a read per hit, per leaf, per pop.
 // ---------------------------------------------------------------------------------
+struct DfPlanes {
+    // per axis: min / max ray parameter of the lower (0) and upper (1) half of the node
+    float lo0x, hi0x, lo1x, hi1x, lo0y, hi0y, lo1y, hi1y, lo0z, hi0z, lo1z, hi1z;
+};
+__device__ __forceinline__ void df_axis(float P, float side, float rrd, float bias, float& lo0, float& hi0, float& lo1,
+                                        float& hi1) {
+    const float pb = P + side;              // corner of the upper half = pos + side of the lower half
+    const float a = P * rrd - bias;         // bmin of the lower half
+    const float b = pb * rrd - bias;        // bmax of the lower half = bmin of the upper half
+    const float c = (pb + side) * rrd - bias; // bmax of the upper half
+    // FMNMX instead of the compare-and-select form of GLSL min / max: the two differ only in the
+    // sign of a zero result (no NaNs here: rrd and the corners are finite), and a zero of either sign
+    // gives the same hit decision and the same chord
+    lo0 = fminf(a, b), hi0 = fmaxf(a, b);
+    lo1 = fminf(b, c), hi1 = fmaxf(b, c);
+}
+__device__ __forceinline__ void df_planes(f3 P, float side, f3 rrd, f3 bias, DfPlanes& q) {
+    df_axis(P.x, side, rrd.x, bias.x, q.lo0x, q.hi0x, q.lo1x, q.hi1x);
+    df_axis(P.y, side, rrd.y, bias.y, q.lo0y, q.hi0y, q.lo1y, q.hi1y);
+    df_axis(P.z, side, rrd.z, bias.z, q.lo0z, q.hi0z, q.lo1z, q.hi1z);
+}
+// (t_min, t_max) of child c (x = bit 2, y = bit 1, z = bit 0), svo_df.comp:27-31
+__device__ __forceinline__ void df_child(const DfPlanes& q, uint32_t c, float& t_min, float& t_max) {
+    const bool bx = (c & 4u) != 0u, by = (c & 2u) != 0u, bz = (c & 1u) != 0u;
+    t_min = fmaxf(bx ? q.lo1x : q.lo0x, fmaxf(by ? q.lo1y : q.lo0y, bz ? q.lo1z : q.lo0z));
+    t_max = fminf(bx ? q.hi1x : q.hi0x, fminf(by ? q.hi1y : q.hi0y, bz ? q.hi1z : q.hi0z));
+}
+__device__ __forceinline__ uint32_t df_hit_mask(const DfPlanes& q) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < 8u; ++c) {
+        float t_min, t_max;
+        df_child(q, c, t_min, t_max); // c is a compile-time constant here: the selects fold away
+        if (t_min < t_max && t_max > 0.0f) mask |= 1u << c;
+    }
+    return mask;
+}
+
 template <bool STATS, bool STRICT, int LEVELS>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kernel(const __grid_constant__ FrameParams p) {
-    __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS]; // [level][thread]
+    __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS]; // [level][thread] = (node, todo | depth << 8)
     uint32_t ix, iy;
     thread_pixel(p, ix, iy);
     if (ix >= p.out_w || iy >= p.out_h) return;
@@ -852,60 +900,68 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
     const f3 bias = F3(rrd.x * ro.x, rrd.y * ro.y, rrd.z * ro.z);
 
     int sp = 0;
-    uint32_t node = 0, child_idx = 0, depth = 0; // depth of `node`
-    f3 pos = F3(0.f, 0.f, 0.f);
-    float side = 0.5f;
+    uint32_t node = 0, depth = 0; // depth of `node`
+    f3 P = F3(0.f, 0.f, 0.f);     // corner of `node`
+    float side = 0.5f;            // side of its children
     Accum<STRICT> acc;
     const uint32_t stack = stack_base(stack_mem);
 
-    for (;;) {
-        st.step();
-        st.read(4); // children[child_idx]
-        const uint32_t s = load_word(p.cnodes, node, child_idx);
-        const f3 bmin = F3(pos.x * rrd.x - bias.x, pos.y * rrd.y - bias.y, pos.z * rrd.z - bias.z);
-        const f3 bmax = F3((pos.x + side) * rrd.x - bias.x, (pos.y + side) * rrd.y - bias.y,
-                           (pos.z + side) * rrd.z - bias.z);
-        const float t_min = max_elem(F3(gmin(bmin.x, bmax.x), gmin(bmin.y, bmax.y), gmin(bmin.z, bmax.z)));
-        const float t_max = min_elem(F3(gmax(bmin.x, bmax.x), gmax(bmin.y, bmax.y), gmax(bmin.z, bmax.z)));
+    DfPlanes q;
+    df_planes(P, side, rrd, bias, q);
+    uint32_t todo = df_hit_mask(q); // hit children of `node` not visited yet
+    if (STATS) {
+        st.steps += 8;
+        st.read(32 + 4 * __popc(todo)); // children[i] of every iteration + is_leaf_depth of the hit ones
+    }
 
-        if (t_min < t_max && t_max > 0.0f) {
-            st.read(4); // nodes[child].is_leaf_depth
-            if (word_is_leaf(s)) {
-                st.read(4); // color
-                acc.add(s, t_max - gmax(t_min, 0.0f));
-            } else {
-                if (child_idx != 7u) {
-                    if (sp < LEVELS) stack_store(stack, (uint32_t)sp, node, child_idx | (depth << 3));
-                    ++sp;
-                }
-                side *= 0.5f;
-                node = s;
-                ++depth; // a child is one level below its parent (also in DAGs: shared subtrees have one size)
-                child_idx = 0;
-                continue;
+    for (;;) {
+        if (todo == 0u) {
+            // node finished: back to the nearest ancestor with children left
+            if (sp == 0) break;
+            --sp;
+            const uint2 e = stack_load(stack, (uint32_t)min(sp, LEVELS - 1));
+            node = e.x;
+            todo = e.y & 0xFFu;
+            depth = e.y >> 8;
+            const float size = __int_as_float((127 - (int)depth) << 23); // exp2(-depth): the node's side
+            side = size * 0.5f;
+            // corner of the node: the corner of any descendant rounded down to a multiple of its size
+            // (levels left by tail descents pushed nothing, so there is no per-level offset to undo)
+            const float rsize = pow2_reciprocal(size);
+            P = F3(size * floorf(P.x * rsize), size * floorf(P.y * rsize), size * floorf(P.z * rsize));
+            df_planes(P, side, rrd, bias, q);
+            continue;
+        }
+        const uint32_t c = (uint32_t)__ffs((int)todo) - 1u;
+        todo &= todo - 1u;
+        const uint32_t s = load_word(p.cnodes, node, c);
+        if (word_is_leaf(s)) {
+            float t_min, t_max;
+            df_child(q, c, t_min, t_max);
+            st.read(4); // color
+            acc.add(s, t_max - fmaxf(t_min, 0.0f));
+        } else {
+            // the shader pushes unless this is child 7 and pops when the subtree is done (one read of
+            // nodes[node].is_leaf_depth per pop, svo_df.comp:58); here the entry is only needed when
+            // hit children remain
+            if (c != 7u) st.read(4);
+            if (todo != 0u) {
+                stack_store(stack, (uint32_t)min(sp, LEVELS - 1), node, todo | (depth << 8));
+                ++sp;
+            }
+            if (c & 4u) P.x += side;
+            if (c & 2u) P.y += side;
+            if (c & 1u) P.z += side;
+            node = s;
+            ++depth;
+            side *= 0.5f;
+            df_planes(P, side, rrd, bias, q);
+            todo = df_hit_mask(q);
+            if (STATS) {
+                st.steps += 8;
+                st.read(32 + 4 * __popc(todo));
             }
         }
-
-        if (child_idx == 7u) {
-            --sp;
-            if (sp < 0) break;
-            const uint2 e = stack_load(stack, (uint32_t)sp);
-            node = e.x;
-            child_idx = e.y & 7u;
-            depth = e.y >> 3;
-            st.read(4); // nodes[node].is_leaf_depth (svo_df.comp:58)
-            side = __int_as_float((127 - (int)depth) << 23) * 0.5f; // exp2(-depth) * 0.5
-        }
-
-        const float s2 = side * 2.0f;
-        const float rs2 = pow2_reciprocal(s2);
-        pos.x -= gmod_pow2(pos.x, s2, rs2);
-        pos.y -= gmod_pow2(pos.y, s2, rs2);
-        pos.z -= gmod_pow2(pos.z, s2, rs2);
-        ++child_idx;
-        if (child_idx & 4u) pos.x += side;
-        if (child_idx & 2u) pos.y += side;
-        if (child_idx & 1u) pos.z += side;
     }
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
 }

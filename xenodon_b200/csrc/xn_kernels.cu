@@ -51,6 +51,10 @@
 #ifndef XN_TEX_MIN_BLOCKS
 #define XN_TEX_MIN_BLOCKS 6
 #endif
+// svo_df: hit mask of a node accumulated with comparison flags and FMAs
+#ifndef XN_DF_FLAG_MASK
+#define XN_DF_FLAG_MASK 1
+#endif
 // ESVO PUSH: 1 = always write the stack entry, 0 = only when the child exits before its parent (`h`)
 #ifndef XN_ESVO_ALWAYS_STORE
 #define XN_ESVO_ALWAYS_STORE 1
@@ -883,6 +887,19 @@ __device__ __forceinline__ void df_child(const DfPlanes& q, uint32_t c, float& t
     t_max = fminf(bx ? q.hi1x : q.hi0x, fminf(by ? q.hi1y : q.hi0y, bz ? q.hi1z : q.hi0z));
 }
 __device__ __forceinline__ uint32_t df_hit_mask(const DfPlanes& q) {
+#if XN_DF_FLAG_MASK
+    // hit bits accumulated as a float on the FMA pipe: each test is two 1.0 / 0.0 comparison flags,
+    // their product is the hit, and mask += hit * 2^c is exact (the kernel is ALU-pipe bound)
+    float maskf = 0.0f;
+#pragma unroll
+    for (uint32_t c = 0; c < 8u; ++c) {
+        float t_min, t_max, f1, f2;
+        df_child(q, c, t_min, t_max); // c is a compile-time constant here: the selects fold away
+        asm("set.lt.f32.f32 %0, %2, %3;\n\tset.gt.f32.f32 %1, %3, 0f00000000;" : "=f"(f1), "=f"(f2) : "f"(t_min), "f"(t_max));
+        maskf = __fmaf_rn(f1 * f2, (float)(1u << c), maskf);
+    }
+    return (uint32_t)maskf;
+#else
     uint32_t mask = 0;
 #pragma unroll
     for (uint32_t c = 0; c < 8u; ++c) {
@@ -891,6 +908,7 @@ __device__ __forceinline__ uint32_t df_hit_mask(const DfPlanes& q) {
         if (t_min < t_max && t_max > 0.0f) mask |= 1u << c;
     }
     return mask;
+#endif
 }
 
 template <bool STATS, bool STRICT, int LEVELS>

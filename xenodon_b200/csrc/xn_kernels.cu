@@ -55,6 +55,10 @@
 #ifndef XN_DF_FLAG_MASK
 #define XN_DF_FLAG_MASK 1
 #endif
+// node slab test of svo_naive / svo_rope with FMNMX
+#ifndef XN_SLAB_FMNMX
+#define XN_SLAB_FMNMX 1
+#endif
 // ESVO PUSH: 1 = always write the stack entry, 0 = only when the child exits before its parent (`h`)
 #ifndef XN_ESVO_ALWAYS_STORE
 #define XN_ESVO_ALWAYS_STORE 1
@@ -797,9 +801,18 @@ __device__ __forceinline__ void node_slab(f3 offset, float side, f3 rrd, f3 bias
     const f3 nmin = F3(offset.x * rrd.x - bias.x, offset.y * rrd.y - bias.y, offset.z * rrd.z - bias.z);
     const f3 nmax = F3((offset.x + side) * rrd.x - bias.x, (offset.y + side) * rrd.y - bias.y,
                        (offset.z + side) * rrd.z - bias.z);
+#if XN_SLAB_FMNMX
+    // FMNMX instead of the compare-and-select form of GLSL min / max: they differ only in the sign
+    // of a zero result (no NaNs: rrd, offsets and bias are finite), and a zero of either sign gives
+    // the same comparisons and the same chord; 8 instructions instead of 26
+    far = F3(fmaxf(nmin.x, nmax.x), fmaxf(nmin.y, nmax.y), fmaxf(nmin.z, nmax.z));
+    u_min = fmaxf(fminf(nmin.x, nmax.x), fmaxf(fminf(nmin.y, nmax.y), fminf(nmin.z, nmax.z)));
+    u_max = fminf(far.x, fminf(far.y, far.z));
+#else
     far = F3(gmax(nmin.x, nmax.x), gmax(nmin.y, nmax.y), gmax(nmin.z, nmax.z));
     u_min = max_elem(F3(gmin(nmin.x, nmax.x), gmin(nmin.y, nmax.y), gmin(nmin.z, nmax.z)));
     u_max = min_elem(far);
+#endif
 }
 
 // ---------------------------------------------------------------------------------
@@ -832,8 +845,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_naive_ke
             float u_min, u_max;
             f3 far;
             node_slab(offset, side, rrd, bias, u_min, u_max, far);
-            u_min = gmax(u_min, 0.0f);
-            const float step = gmax(u_max - u_min, MIN_STEP_SIZE);
+            // fmaxf: same values as GLSL max here (finite operands; a zero's sign cannot reach the image)
+            u_min = fmaxf(u_min, 0.0f);
+            const float step = fmaxf(u_max - u_min, MIN_STEP_SIZE);
             t += step;
 
             st.read(4); // color
@@ -1298,14 +1312,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_rope_ker
             float u_min, u_max;
             f3 far;
             node_slab(offset, side, rrd, bias, u_min, u_max, far);
-            const float step = u_max - gmax(u_min, 0.0f);
+            const float step = u_max - (XN_SLAB_FMNMX ? fmaxf(u_min, 0.0f) : gmax(u_min, 0.0f));
             st.read(4); // color
             acc.add(meta, step);
             st.step();
 
             // neighbor_index, svo_rope.comp:50-63 (ties go to the later axis)
             uint32_t n;
-            if (far.x < gmin(far.y, far.z)) {
+            if (far.x < fminf(far.y, far.z)) {
                 n = nbx;
                 offset.x += sgn.x * side;
             } else if (far.y < far.z) {

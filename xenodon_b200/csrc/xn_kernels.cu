@@ -1339,9 +1339,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_rope_ker
             pos = F3(ro.x + u_max * rd.x, ro.y + u_max * rd.y, ro.z + u_max * rd.z);
             side = __int_as_float((127 - (int)meta_depth(meta)) << 23); // exp2(-depth)
             const float rside = pow2_reciprocal(side);
-            offset.x = offset.x - gmod_pow2(offset.x, side, rside);
-            offset.y = offset.y - gmod_pow2(offset.y, side, rside);
-            offset.z = offset.z - gmod_pow2(offset.z, side, rside);
+            // offset -= mod(offset, side) (svo_rope.comp:38).  k = floor(offset / side) is an integer,
+            // side * k is exact, and so are offset - side * k (a multiple of ulp(offset) below offset)
+            // and offset minus that: the result is side * k itself, three operations instead of five
+            offset.x = side * floorf(offset.x * rside);
+            offset.y = side * floorf(offset.y * rside);
+            offset.z = side * floorf(offset.z * rside);
             descend(p.nodes, pos, node, meta, offset, side, st);
         }
     }

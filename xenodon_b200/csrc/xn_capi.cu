@@ -102,6 +102,8 @@ struct xn_ctx {
     uint64_t nx = 0, ny = 0, nz = 0;
     xn::DNode* nodes = nullptr;  // file-order 64-byte records (svo_rope)
     xn::CNode* cnodes = nullptr; // compact level-order records of the internal nodes (the other three)
+    uint32_t* top_table = nullptr; // svo_naive entry table
+    uint32_t top_levels = 0;
     uint64_t node_count = 0, internal_count = 0, side = 0;
     uint32_t root_meta = 0, max_depth = 0;
     bool grid_has_black_background = false;
@@ -143,8 +145,10 @@ struct xn_ctx {
     void free_nodes() {
         if (nodes) cudaFree(nodes);
         if (cnodes) cudaFree(cnodes);
+        if (top_table) cudaFree(top_table);
         nodes = nullptr;
         cnodes = nullptr;
+        top_table = nullptr;
         node_count = internal_count = side = 0;
     }
 };
@@ -211,6 +215,8 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.nz = (uint32_t)ctx->nz;
     p.nodes = ctx->nodes;
     p.cnodes = ctx->cnodes;
+    p.top_table = ctx->top_table;
+    p.top_levels = ctx->top_levels;
     p.root_meta = ctx->root_meta;
     p.max_depth = ctx->max_depth;
     p.il_count = ctx->il_count;
@@ -417,6 +423,13 @@ void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) 
     }
     apply_l2_window(ctx);
     ctx->root_meta = xn::make_meta(root[0], root[1]);
+    // svo_naive entry table over the first min(tree depth, TOP_LEVELS_MAX) levels
+    ctx->top_levels = std::min<uint32_t>(maxd, xn::TOP_LEVELS_MAX);
+    if (const char* e = std::getenv("XN_TOP_LEVELS")) // tuning knob
+        ctx->top_levels = std::min<uint32_t>({(uint32_t)std::strtoul(e, nullptr, 10), maxd, 9u});
+    XN_CUDA(cudaMalloc(&ctx->top_table, sizeof(uint32_t) << (3 * ctx->top_levels)));
+    XN_CUDA(xn::launch_top_table(ctx->cnodes, ctx->root_meta, ctx->top_levels, ctx->top_table, ctx->stream));
+    XN_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->max_depth = maxd;
     ctx->node_count = count;
     ctx->side = side;

@@ -39,6 +39,11 @@ struct __align__(32) CNode {
 };
 static_assert(sizeof(CNode) == 32, "compact node must be 32 bytes");
 
+// svo_naive entry table: at most this many levels of the tree are folded into it (8: 64 MiB)
+#ifndef XN_TOP_LEVELS_MAX
+#define XN_TOP_LEVELS_MAX 8
+#endif
+constexpr uint32_t TOP_LEVELS_MAX = XN_TOP_LEVELS_MAX;
 constexpr uint32_t META_LEAF = 0x80000000u;
 __host__ __device__ inline uint32_t make_meta(uint32_t color, uint32_t is_leaf_depth) {
     return (is_leaf_depth & META_LEAF) | ((is_leaf_depth & 0x1Fu) << 24) | (color & 0x00FFFFFFu);
@@ -74,6 +79,11 @@ struct FrameParams {
     unsigned long long tex_unorm, tex_raw;
     const DNode* nodes;   // svo_rope (and the file-order view of the tree)
     const CNode* cnodes;  // svo_naive, svo_df, esvo
+    // svo_naive: what find() reaches after its first top_levels levels, for each of the
+    // 2^(3 top_levels) aligned cells of the cube (a leaf word, or the word offset of an internal
+    // node), index = cx << 2 top_levels | cy << top_levels | cz; top_levels = min(tree depth, 8)
+    const uint32_t* top_table;
+    uint32_t top_levels;
     uint32_t root_meta;
     uint32_t max_depth;     // deepest node depth in the tree (stack sizing)
 

@@ -59,6 +59,10 @@
 #ifndef XN_SLAB_FMNMX
 #define XN_SLAB_FMNMX 1
 #endif
+// svo_naive: first TOP_LEVELS levels of find() from the entry table
+#ifndef XN_NAIVE_TOP_TABLE
+#define XN_NAIVE_TOP_TABLE 1
+#endif
 // ESVO PUSH: 1 = always write the stack entry, 0 = only when the child exits before its parent (`h`)
 #ifndef XN_ESVO_ALWAYS_STORE
 #define XN_ESVO_ALWAYS_STORE 1
@@ -840,6 +844,32 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_naive_ke
             uint32_t node = 0, meta = p.root_meta;
             f3 offset = F3(0.f, 0.f, 0.f);
             float side = 1.0f;
+#if XN_NAIVE_TOP_TABLE
+            {
+                // The shader's find() starts at the root (svo_naive.comp:50-52).  Each of its decisions,
+                // `pos >= offset + extent`, compares against an odd multiple of the child size, so the
+                // child taken at level l is bit l of the coordinate's binary expansion -- for any
+                // binary32 pos: pos < 0 fails every comparison (bits 0), pos >= 1 passes every one
+                // (bits 1).  The first K = min(depth, 8) levels are therefore a function of the cell
+                // floor(pos * 2^K), looked up in a table built at upload: one load replaces K
+                // dependent ones, and offset = cell * 2^-depth is the same exact sum of powers of
+                // two the shader accumulates.  The instrumented build counts the reads of those levels.
+                const uint32_t K = p.top_levels;
+                const int cells = 1 << K;
+                const float fcells = (float)cells;
+                const int cx = min(max(__float2int_rd(pt.x * fcells), 0), cells - 1);
+                const int cy = min(max(__float2int_rd(pt.y * fcells), 0), cells - 1);
+                const int cz = min(max(__float2int_rd(pt.z * fcells), 0), cells - 1);
+                const uint32_t w = __ldg(p.top_table + (((uint32_t)cx << (2u * K)) | ((uint32_t)cy << K) | (uint32_t)cz));
+                const uint32_t d = word_is_leaf(w) ? meta_depth(w) : K; // levels taken
+                const uint32_t drop = K - d;
+                side = __int_as_float((127 - (int)d) << 23); // exp2(-d)
+                offset = F3((float)(cx >> drop) * side, (float)(cy >> drop) * side, (float)(cz >> drop) * side);
+                node = w;
+                meta = word_is_leaf(w) ? w : 0u;
+                st.read(8u * d); // is_leaf_depth + children[c] of the levels above
+            }
+#endif
             descend(p.cnodes, pt, node, meta, offset, side, st);
 
             float u_min, u_max;

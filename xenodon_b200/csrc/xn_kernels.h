@@ -12,6 +12,9 @@ cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint3
 // compact residency of the octree (internal nodes only, level order); *out is cudaMalloc'ed
 cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, uint64_t* n_internal_out,
                                 cudaStream_t stream);
+// svo_naive entry table (2^(3 levels) words)
+cudaError_t launch_top_table(const CNode* nodes, uint32_t root_meta, uint32_t levels, uint32_t* table,
+                             cudaStream_t stream);
 cudaError_t launch_brick_grid(const uint32_t* linear, uint32_t* bricked, const BrickLayout& L, uint32_t nx, uint32_t ny,
                               uint32_t nz, cudaStream_t stream);
 cudaError_t launch_unbrick_grid(const uint32_t* bricked, uint32_t* linear, const BrickLayout& L, uint32_t nx,

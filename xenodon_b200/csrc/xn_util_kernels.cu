@@ -139,6 +139,33 @@ cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, 
 }
 
 // ---------------------------------------------------------------------------------
+// svo_naive entry table: one thread per cell of the 2^levels grid walks find()'s first `levels`
+// levels (the child at level l is bit l of each cell coordinate) and records where it ends: a
+// leaf word, or the word offset of the internal node at depth `levels`.
+// ---------------------------------------------------------------------------------
+__global__ void top_table_kernel(const CNode* __restrict__ nodes, uint32_t root_meta, uint32_t levels,
+                                 uint32_t* __restrict__ table) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << (3 * levels))) return;
+    const uint32_t m = (1u << levels) - 1u;
+    const uint32_t cz = i & m, cy = (i >> levels) & m, cx = i >> (2 * levels);
+    uint32_t w = (root_meta & META_LEAF) ? root_meta : 0u; // leaf root: its meta; else word offset 0
+    for (uint32_t l = 0; l < levels && !(w & META_LEAF); ++l) {
+        const uint32_t sh = levels - 1u - l;
+        const uint32_t child = (((cx >> sh) & 1u) << 2) | (((cy >> sh) & 1u) << 1) | ((cz >> sh) & 1u);
+        w = reinterpret_cast<const uint32_t*>(nodes)[w | child];
+    }
+    table[i] = w;
+}
+
+cudaError_t launch_top_table(const CNode* nodes, uint32_t root_meta, uint32_t levels, uint32_t* table,
+                             cudaStream_t stream) {
+    const uint32_t n = 1u << (3 * levels);
+    top_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(nodes, root_meta, levels, table);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
 // grid re-layout: x-major linear <-> bricked (xn_brick.h).  One thread per bricked slot, so the
 // bricked side is accessed in order; the linear side is touched in 2x2x2 / 4x4x2 groups that
 // stay inside a few cache lines.  Padding slots are written as 0 (= the border colour).

@@ -1035,9 +1035,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
 }
 
-// ESVO child selection written with predicated PTX (as dda_step): the compiler turns
-// `if (c) { pos += d; idx ^= bit; }` into compare + FADD + FSEL + SEL chains on the ALU pipe,
-// which bounds this kernel (ncu: ALU 70 %, issue 72 %); predicated FADDs run on the FMA pipe.
+// ESVO child selection.  The compiler turns `if (c) { pos += d; idx ^= bit; }` into compare +
+// FADD + FSEL + SEL chains on the ALU pipe, which bounded this kernel (ncu: ALU 70 %, issue 72 %).
+// XN_ESVO_PTX = 2 writes the comparisons as 1.0 / 0.0 flags (`set`) followed by exact FMAs, which
+// run on the FMA pipe; 0 is the plain C++.  (Predicated `@p add` in PTX was tried too: ptxas turns
+// it back into FADD + FSEL.)
 #ifndef XN_ESVO_PTX
 #define XN_ESVO_PTX 2
 #endif
@@ -1066,26 +1068,6 @@ __device__ __forceinline__ uint32_t esvo_advance(float tcorx, float tcory, float
         : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz), "=&f"(fx), "=&f"(fy), "=&f"(fz)
         : "f"(tcorx), "f"(tcory), "f"(tcorz), "f"(tc_max), "f"(-se));
     return m;
-#elif XN_ESVO_PTX
-    uint32_t m;
-    asm("{\n\t"
-        ".reg .pred ax, ay, az;\n\t"
-        ".reg .b32 mx, my, mz;\n\t"
-        "setp.le.f32 ax, %4, %7;\n\t"
-        "setp.le.f32 ay, %5, %7;\n\t"
-        "setp.le.f32 az, %6, %7;\n\t"
-        "@ax sub.f32 %1, %1, %8;\n\t"
-        "@ay sub.f32 %2, %2, %8;\n\t"
-        "@az sub.f32 %3, %3, %8;\n\t"
-        "selp.b32 mx, 4, 0, ax;\n\t"
-        "selp.b32 my, 2, 0, ay;\n\t"
-        "selp.b32 mz, 1, 0, az;\n\t"
-        "lop3.b32 %0, mx, my, mz, 0xFE;\n\t"
-        "}"
-        : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
-        : "f"(tcorx), "f"(tcory), "f"(tcorz), "f"(tc_max), "f"(se));
-    fx = (m & 4u) ? 1.0f : 0.0f, fy = (m & 2u) ? 1.0f : 0.0f, fz = (m & 1u) ? 1.0f : 0.0f;
-    return m;
 #else
     const bool ax = tcorx <= tc_max, ay = tcory <= tc_max, az = tcorz <= tc_max;
     if (ax) posx -= se;
@@ -1111,25 +1093,6 @@ __device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, f
         "fma.rn.f32 mf, ax, 0f40800000, az;\n\t"
         "fma.rn.f32 mf, ay, 0f40000000, mf;\n\t"
         "cvt.rzi.u32.f32 %0, mf;\n\t"
-        "}"
-        : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
-        : "f"(tcenx), "f"(tceny), "f"(tcenz), "f"(t_min), "f"(se));
-    return m;
-#elif XN_ESVO_PTX
-    uint32_t m;
-    asm("{\n\t"
-        ".reg .pred ax, ay, az;\n\t"
-        ".reg .b32 mx, my, mz;\n\t"
-        "setp.gt.f32 ax, %4, %7;\n\t"
-        "setp.gt.f32 ay, %5, %7;\n\t"
-        "setp.gt.f32 az, %6, %7;\n\t"
-        "@ax add.f32 %1, %1, %8;\n\t"
-        "@ay add.f32 %2, %2, %8;\n\t"
-        "@az add.f32 %3, %3, %8;\n\t"
-        "selp.b32 mx, 4, 0, ax;\n\t"
-        "selp.b32 my, 2, 0, ay;\n\t"
-        "selp.b32 mz, 1, 0, az;\n\t"
-        "lop3.b32 %0, mx, my, mz, 0xFE;\n\t"
         "}"
         : "=r"(m), "+f"(posx), "+f"(posy), "+f"(posz)
         : "f"(tcenx), "f"(tceny), "f"(tcenz), "f"(t_min), "f"(se));

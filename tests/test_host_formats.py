@@ -305,3 +305,36 @@ def test_bricked_layout_index_function(xb, dims):
             assert (d[i + 1] - 1) & 0xFFFFFFFFFFFFFFFF & mask == d[i]          # -1: K = -1
     # a forced top axis (the 64-bit cursor wants z on top) is honoured
     assert xb.brick_layout(nx, ny, nz, 2)["top"] == 2
+
+
+def test_ingest_plan_of_tiff_layouts(xb, tmp_path):
+    """What the streaming ingest (xn_upload_grid_tiff) decides per file, checked without a GPU: strip
+    files of one sample layout stream (adjacent strips merge into one read per layer), tiled or
+    mixed-layout files fall back to the host decoder, and the decode flags follow libtiff's rules."""
+    from util import write_tiff
+    rng = np.random.default_rng(8)
+    layers = [rng.integers(0, 256, (12, 10, 4), dtype=np.uint8) for _ in range(3)]
+    p = tmp_path / "strips.tif"
+    write_tiff(p, layers, photometric=2, extra=2, rows_per_strip=5)
+    info = xb.tiff_stream_info(p)
+    assert info == {"streamable": True, "samples": 4, "photometric": 2, "has_alpha": True, "unassociated": True,
+                    "flip": True, "runs": 3}
+    write_tiff(p, layers, photometric=2, extra=1, orientation=4)
+    info = xb.tiff_stream_info(p)
+    assert info["streamable"] and not info["unassociated"] and not info["flip"]
+    grey = [a[..., :2].copy() for a in layers]
+    write_tiff(p, grey, photometric=1, extra=None)  # second sample not declared alpha: ignored
+    info = xb.tiff_stream_info(p)
+    assert info["streamable"] and info["samples"] == 2 and not info["has_alpha"]
+    write_tiff(p, grey, photometric=0, extra=2)      # grey + unassociated alpha: alpha kept, no pre-multiplication
+    info = xb.tiff_stream_info(p)
+    assert info["has_alpha"] and not info["unassociated"] and info["photometric"] == 0
+    write_tiff(p, layers, photometric=2, extra=2, tile=(16, 16))
+    assert not xb.tiff_stream_info(p)["streamable"]
+    # our own writer's files stream, one run per layer
+    g = rng.integers(0, 256, (4, 6, 5, 4), dtype=np.uint8)
+    xb.Grid(g).save_tiff(p)
+    info = xb.tiff_stream_info(p)
+    assert info["streamable"] and info["runs"] == 4 and info["samples"] == 4
+    with pytest.raises(xb.XenodonError, match="Failed to open"):
+        xb.tiff_stream_info(tmp_path / "missing.tif")

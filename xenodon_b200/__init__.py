@@ -78,6 +78,7 @@ _PROTOTYPES = {
     "xn_ctx_device": (C.c_int, [C.c_void_p]),
     "xn_upload_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "xn_upload_svo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "xn_tiff_stream_info": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "xn_upload_grid_tiff": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "xn_upload_grid_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "xn_upload_svo_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
@@ -225,6 +226,14 @@ class Octree:
 
     def save_svo(self, path):
         _check(lib().xn_svo_write(os.fsencode(path), self.nodes.ctypes.data, len(self.nodes), self.side))
+
+
+def tiff_stream_info(path) -> dict:
+    """How the ingest pipeline will take a TIFF (csrc/host/xn_tiff.cpp tiff_plan)."""
+    ok, fmt, runs = C.c_int(), (C.c_uint32 * 5)(), C.c_uint64()
+    _check(lib().xn_tiff_stream_info(os.fsencode(path), C.byref(ok), fmt, C.byref(runs)))
+    return {"streamable": bool(ok.value), "samples": fmt[0], "photometric": fmt[1], "has_alpha": bool(fmt[2]),
+            "unassociated": bool(fmt[3]), "flip": bool(fmt[4]), "runs": runs.value}
 
 
 def brick_layout(nx: int, ny: int, nz: int, top: int = -1) -> dict:

@@ -1254,6 +1254,24 @@ int xn_tiff_info(const char* path, uint64_t dims_out[3]) {
         dims_out[2] = info.nz;
     });
 }
+int xn_tiff_stream_info(const char* path, int* streamable_out, uint32_t format_out[5], uint64_t* runs_out) {
+    return guarded([&] {
+        if (!path || !streamable_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        const xn::TiffPlan plan = xn::tiff_plan(path);
+        *streamable_out = plan.streamable ? 1 : 0;
+        if (format_out) {
+            format_out[0] = plan.format.samples;
+            format_out[1] = plan.format.photometric;
+            format_out[2] = plan.format.has_alpha;
+            format_out[3] = plan.format.unassociated;
+            format_out[4] = plan.format.flip;
+        }
+        if (runs_out) {
+            *runs_out = 0;
+            for (const auto& sl : plan.slices) *runs_out += sl.size();
+        }
+    });
+}
 int xn_tiff_read(const char* path, uint8_t* rgba_out, uint64_t cap_bytes) {
     return guarded([&] {
         if (!path || !rgba_out) throw xn::Error(XN_ERR_INVALID, "null argument");

@@ -63,10 +63,6 @@
 #ifndef XN_NAIVE_TOP_TABLE
 #define XN_NAIVE_TOP_TABLE 1
 #endif
-// ESVO: a 10-level stack instantiation for trees up to 512^3
-#ifndef XN_ESVO_SMALL_STACK
-#define XN_ESVO_SMALL_STACK 0
-#endif
 // ESVO PUSH: 1 = always write the stack entry, 0 = only when the child exits before its parent (`h`)
 #ifndef XN_ESVO_ALWAYS_STORE
 #define XN_ESVO_ALWAYS_STORE 1
@@ -1387,9 +1383,7 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
             break;
         case 1: svo_naive_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p); break;
         case 2:
-            // stack levels: what they take from shared memory is carved out of the L1
             if (deep) esvo_kernel<STATS, STRICT, 24><<<grid, block, 0, stream>>>(p);
-            else if (XN_ESVO_SMALL_STACK && p.max_depth + 1u <= 10u) esvo_kernel<STATS, STRICT, 10><<<grid, block, 0, stream>>>(p);
             else esvo_kernel<STATS, STRICT, 12><<<grid, block, 0, stream>>>(p);
             break;
         case 3:

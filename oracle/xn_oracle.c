@@ -641,15 +641,17 @@ int xo_render(int traversal, const xo_volume* vol, const xo_params* params, cons
 #endif
     (void)nt;
     const int64_t H = output->h, W = output->w;
-#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
-    for (int64_t y = 0; y < H; ++y) {
-        for (int64_t x = 0; x < W; ++x) {
-            ray_stats st = {0, 0};
-            uint32_t px = shade_pixel(&c, traversal, (uint32_t)x, (uint32_t)y, &st);
-            rgba_out[y * W + x] = px;
-            if (steps_out) steps_out[y * W + x] = st.steps;
-            if (bytes_out) bytes_out[y * W + x] = st.bytes;
-        }
+    /* parallel over pixels in chunks of 64 (not over rows: the benchmark samples 8-row bands, which
+     * would keep only two threads busy) */
+    const int64_t N = W * H;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nt)
+    for (int64_t i = 0; i < N; ++i) {
+        const int64_t y = i / W, x = i - y * W;
+        ray_stats st = {0, 0};
+        uint32_t px = shade_pixel(&c, traversal, (uint32_t)x, (uint32_t)y, &st);
+        rgba_out[i] = px;
+        if (steps_out) steps_out[i] = st.steps;
+        if (bytes_out) bytes_out[i] = st.bytes;
     }
     return 0;
 }

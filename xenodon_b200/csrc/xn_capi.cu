@@ -349,7 +349,15 @@ void apply_layout(xn_ctx* ctx) {
                                               (uint32_t)ctx->nz, ctx->stream));
                 XN_CUDA(cudaStreamSynchronize(ctx->stream));
             } else if (want == XN_GRID_LAYOUT_TEXTURE) {
-                make_texture(ctx);
+                try {
+                    make_texture(ctx);
+                } catch (const CudaError&) {
+                    // AUTO only optimises: when the array does not fit beside the linear copy, the
+                    // linear copy stays in use (an explicit request for the texture residency fails)
+                    if (ctx->layout_mode != XN_GRID_LAYOUT_AUTO) throw;
+                    cudaGetLastError();
+                    return;
+                }
             }
         }
         if (want != XN_GRID_LAYOUT_LINEAR) {

@@ -709,33 +709,41 @@ void convert(const std::vector<const char*>& args) {
     const uint64_t voxels = dims[0] * dims[1] * dims[2];
     std::printf("%llux%llux%llu = %llu pixels\n", (unsigned long long)dims[0], (unsigned long long)dims[1],
                 (unsigned long long)dims[2], (unsigned long long)voxels);
-    grid.resize(voxels * 4);
-    if (xn_tiff_read(src.c_str(), grid.data(), grid.size()) != XN_OK) {
-        std::printf("Error reading '%s': %s\n", src.c_str(), xn_last_error());
-        return;
-    }
-    std::printf("Source grid:\n Dimensions: %llux%llux%llu\n Size: %llu bytes\n", (unsigned long long)dims[0],
-                (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)(voxels * 4));
-
-    std::printf("Converting to octree...\n");
-    std::fflush(stdout);
     xn_node* nodes = nullptr;
     uint64_t count = 0, side = 0;
     xn_build_stats st{};
     const int type = dag ? 1 : rope ? 2 : 0;
     // The GPU builder (byte-identical output) handles --chan-diff for sparse and rope trees; --dag,
-    // --std-dev, --host, or the absence of a CUDA device use the host builder.
+    // --std-dev, --host, or the absence of a CUDA device use the host builder.  On the GPU path the
+    // volume goes from the file to the device through the ingest pipeline and never exists on the host.
     int rc = XN_ERR_INVALID;
     bool on_gpu = false;
     int n_devices = 0;
     if (!host_only && stddev < 0 && !dag && xn_device_count(&n_devices) == XN_OK && n_devices > 0) {
         xn_ctx* ctx = nullptr;
         if (xn_ctx_create(0, &ctx) == XN_OK) {
-            if (xn_upload_grid(ctx, grid.data(), dims[0], dims[1], dims[2]) == XN_OK)
+            xn_set_grid_layout(ctx, XN_GRID_LAYOUT_LINEAR); // the builder reads the x-major copy
+            if (xn_upload_grid_tiff(ctx, src.c_str(), nullptr, nullptr) == XN_OK) {
+                std::printf("Source grid:\n Dimensions: %llux%llux%llu\n Size: %llu bytes\n", (unsigned long long)dims[0],
+                            (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)(voxels * 4));
+                std::printf("Converting to octree...\n");
+                std::fflush(stdout);
                 rc = xn_convert_resident_grid(ctx, std::max(channel_difference, 0), type, 0, &nodes, &count, &side, &st);
+            }
             xn_ctx_destroy(ctx);
             on_gpu = rc == XN_OK;
         }
+    }
+    if (!on_gpu) {
+        grid.resize(voxels * 4);
+        if (xn_tiff_read(src.c_str(), grid.data(), grid.size()) != XN_OK) {
+            std::printf("Error reading '%s': %s\n", src.c_str(), xn_last_error());
+            return;
+        }
+        std::printf("Source grid:\n Dimensions: %llux%llux%llu\n Size: %llu bytes\n", (unsigned long long)dims[0],
+                    (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)(voxels * 4));
+        std::printf("Converting to octree...\n");
+        std::fflush(stdout);
     }
     if (!on_gpu)
         rc = stddev >= 0

@@ -2,26 +2,41 @@
 """bench.py -- Mrays/s of the volume-traversal path on synthetic volumes of the BASELINE shapes.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload cfg1|cfg2|cfg3|cfg4|cfg5] [--traversal NAME] [--gather ipc|nccl]
+                    [--workload cfg1|cfg2|cfg3|cfg3r|cfg4|cfg4e|cfg5] [--traversal NAME]
+                    [--gather host|ipc|nccl] [--weak] [--no-extras]
 
-A "step" is one frame: one pass of the traversal kernel over every pixel of the frame, with
-the camera of the workload's script (frame i of the script on step i).  Timed region = K
-frames back to back with the volume already resident in HBM (the reference's own benchmark
-recipe: --discard-output, README.md:85-89), device-timed, max over ranks.  `e2e` = the same
-frames through the public C-ABI call with the camera coming from host memory and the finished
-RGBA8 frame copied back to pinned host memory every step.
+A "step" is one frame: one pass of the traversal kernel over every pixel of the frame.  The K
+steps are spread over the WHOLE camera script of the workload (frame floor(i * len / K) on step
+i, the reference's own benchmark recipe runs the whole file: README.md:85-89), so that exterior,
+fly-over and interior views are all sampled whatever K is.
 
-N > 1 (torchrun, one process per GPU): the frame is split by screen region across the GPUs --
-16-row stripes dealt round-robin, the partition a headless.conf with many `device {}` blocks
-expresses -- with the volume replicated, and every GPU's kernel stores its finished pixels
-straight into rank 0's frame buffer over NVLink (CUDA IPC peer memory; --gather nccl uses an
-NCCL gather of contiguous bands instead).  Frame size grows with N (rays per GPU fixed = weak).
+Defaults (BASELINE.json):
+  --gpus 1   cfg4: DDA through the 2048^3 RGBA8 grid (32 GiB, beyond the reference's 4 GB binding
+             limit) at 3840x2160 over camera.txt -- the largest single-GPU configuration.  The same
+             line carries `per_config`: cfg1, cfg2 (every traversal), cfg3, cfg3r and cfg4e measured
+             the same way in the same process.
+  --gpus N   cfg5 STRONG: one 7680x4320 frame of the 1024^3 volume split by screen region over
+             the N GPUs (camera-rotate.txt), volume replicated.
+
+`value` = rays of the K frames / device time of the K back-to-back launches with the volume
+resident in HBM (the reference's --discard-output recipe), max over ranks.  `e2e` = the same
+frames through the public C-ABI call with the camera coming from host memory and every finished
+RGBA8 frame delivered to page-locked host memory, wall-clocked between barriers.
+
+N > 1 (torchrun, one process per GPU): 16-row stripes dealt round-robin over the ranks (the
+partition a headless.conf with many `device {}` blocks expresses).  In the kernel-timed region every
+rank's kernel stores its finished pixels straight into rank 0's frame over NVLink (CUDA IPC peer
+memory).  In the e2e region (--gather host, default) every rank copies its own stripes into ONE
+page-locked host frame shared by all ranks (POSIX shared memory registered with CUDA in every
+process), so the frame leaves over N PCIe links instead of rank 0's one; completion is signalled
+per rank by a stream-ordered flag in the same shared memory, no collective and no host
+synchronisation inside the loop.  --gather ipc / nccl keep the NVLink-gather-then-one-link and the
+NCCL baselines.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -41,19 +56,21 @@ WORKLOADS = {
     "cfg1": dict(volume=("bunny", 512, 361, 512), frame=(1920, 1080), camera="camera-single", traversal="dda",
                  desc="DDA, V-bunny 512x361x512 RGBA8 grid, 1920x1080, camera-single"),
     "cfg2": dict(volume=("bunny", 512, 361, 512), frame=(1920, 1080), camera="camera", traversal="esvo",
-                 desc="ESVO, V-bunny 512x361x512 as lossless SVO (convert --chan-diff 0), 1920x1080, camera.txt path"),
+                 desc="ESVO, V-bunny 512x361x512 as lossless SVO (convert --chan-diff 0), 1920x1080, whole camera.txt path"),
     "cfg3": dict(volume=("tng", 1024, 1024, 1024), frame=(3840, 2160), camera="camera", traversal="dda",
-                 desc="DDA, V-tng 1024^3 RGBA8 grid (4 GiB), 3840x2160, camera.txt path"),
+                 desc="DDA, V-tng 1024^3 RGBA8 grid (4 GiB), 3840x2160, whole camera.txt path"),
     "cfg3r": dict(volume=("tng", 1024, 1024, 1024), frame=(3840, 2160), camera="camera", traversal="svo-rope",
-                  desc="svo-rope, V-tng 1024^3 as lossless rope SVO (GPU convert --chan-diff 0 --rope), 3840x2160, camera.txt path"),
+                  desc="svo-rope, V-tng 1024^3 as lossless rope SVO (GPU convert --chan-diff 0 --rope), 3840x2160, whole camera.txt path"),
     "cfg4": dict(volume=("tng", 2048, 2048, 2048), frame=(3840, 2160), camera="camera", traversal="dda",
-                 desc="DDA, V-tng 2048^3 RGBA8 grid (32 GiB), 3840x2160, camera.txt path"),
+                 desc="DDA, V-tng 2048^3 RGBA8 grid (32 GiB), 3840x2160, whole camera.txt path"),
     "cfg4e": dict(volume=("tng", 2048, 2048, 2048), frame=(3840, 2160), camera="camera", traversal="esvo",
-                  desc="ESVO, V-tng 2048^3 as lossless SVO (GPU convert --chan-diff 0), 3840x2160, camera.txt path"),
+                  desc="ESVO, V-tng 2048^3 as lossless SVO (GPU convert --chan-diff 0), 3840x2160, whole camera.txt path"),
     "cfg5": dict(volume=("tng", 1024, 1024, 1024), frame=(7680, 4320), camera="camera-rotate", traversal="dda",
-                 desc="DDA, V-tng 1024^3, 7680x4320 split by screen region, camera-rotate"),
+                 desc="DDA, V-tng 1024^3, 7680x4320 split by screen region, whole camera-rotate.txt path"),
 }
 
+KERNEL_NAMES = {"dda": "dda_kernel", "esvo": "esvo_kernel", "svo-rope": "svo_rope_kernel",
+                "svo-df": "svo_df_kernel", "svo-naive": "svo_naive_kernel"}
 
 _JSON_OUT = sys.stdout
 
@@ -65,6 +82,11 @@ def log(*a):
 def frame_for(base, n_gpus, weak):
     from xenodon_b200 import distributed as xd
     return xd.frame_for(base, n_gpus, weak)
+
+
+def frame_schedule(n_script: int, count: int):
+    """Script frame of each of `count` steps: spread evenly over the whole script."""
+    return [(i * n_script) // max(count, 1) for i in range(count)]
 
 
 class ClockSampler:
@@ -111,7 +133,9 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+            # median over the samples taken while the GPU was clocked up (under load)
+            busy = [s for s in sm if s >= 0.5 * max(mx)] or sm
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), samples=len(sm))
         out["reasons"] = sorted(reasons)
         return out
 
@@ -124,12 +148,12 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def measured_traffic(workload, kernel_name):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def profile_entry(workload, kernel_name):
+    """What the committed ncu capture of this workload's dominant kernel says (profiles/traffic.json):
+    DRAM bytes per launch and which unit bounds the kernel."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            e = json.load(f).get(f"{workload}/{kernel_name}")
-        return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]) if e else None
+            return json.load(f).get(f"{workload}/{kernel_name}")
     except Exception:
         return None
 
@@ -144,8 +168,34 @@ def cam_tuple(frames, i):
     return (tuple(f[0]), tuple(f[1]), tuple(f[2]))
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun's OMP_NUM_THREADS=1 does not apply to the CPU arms:
+    they size their own thread pools)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_openmp_threads(n: int) -> int:
+    """The reference shader library (oracle/_ref) is `#pragma omp parallel for`: make its thread
+    count explicit instead of inheriting OMP_NUM_THREADS from the launcher.  Returns what is in force."""
+    import ctypes
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_dynamic(0)
+        gomp.omp_set_num_threads(n)
+        gomp.omp_get_max_threads.restype = ctypes.c_int
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
+
+
 # --------------------------------------------------------------------------------------------
-# reference arm: the CPU oracle (the reference's Vulkan build cannot run here)
+# CPU arms: the reference's own shader text compiled as C++ (oracle/_ref, kind "reference") or the
+# C restatement (oracle/xn_oracle.c, kind "port").  The reference's Vulkan build cannot run here
+# (no loader / ICD / glslc, BASELINE.md section 3).
 # --------------------------------------------------------------------------------------------
 def oracle_sample_rows(h, bands=8, rows_per_band=8):
     """Bounded sample of a frame: `bands` groups of rows spread evenly over the frame height."""
@@ -156,21 +206,18 @@ def oracle_sample_rows(h, bands=8, rows_per_band=8):
     return out
 
 
-def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid, tree, prefer_ref=False):
-    """Times the CPU implementation on a bounded sample of each frame; returns (Mrays/s, info).
-
-    prefer_ref: use oracle/_ref/libxnref_glsl.so -- the reference's OWN shader text compiled as
-    C++ (built where the reference checkout existed; it travels with the repo) -- when present
-    (kind "reference"); otherwise the C restatement oracle/xn_oracle.c (kind "port")."""
+def run_oracle_frames(traversal, frame, cam_list, host_grid, tree, prefer_ref=False, warm=1, bands=None):
+    """Times the CPU implementation on a bounded row sample of each camera in cam_list (the first
+    `warm` are untimed); returns (Mrays/s, info)."""
     from oracle import xo, xref
     use_ref = prefer_ref and xref.available()
     W, H = frame
-    bands = oracle_sample_rows(H)
-    threads = os.cpu_count() or 1
+    bands = bands or oracle_sample_rows(H)
+    threads = host_threads()
+    in_force = set_openmp_threads(threads) if use_ref else threads
     rays = 0
     t_total = 0.0
-    for i in range(warmup + steps):
-        cam = cam_tuple(cams, i)
+    for i, cam in enumerate(cam_list):
         t0 = time.perf_counter()
         for (y0, rows) in bands:
             kw = dict(camera=cam, output=(0, y0, W, rows), display=(0, 0, W, H), emission=EMISSION)
@@ -184,14 +231,152 @@ def run_oracle_frames(workload, traversal, frame, cams, steps, warmup, host_grid
             else:
                 xo.render(traversal, nodes=tree.nodes, side=tree.side, threads=threads, want_stats=False, **kw)
         dt = time.perf_counter() - t0
-        if i >= warmup:
+        if i >= warm:
             t_total += dt
             rays += sum(r for _, r in bands) * W
-    mrays = rays / t_total / 1e6
-    sample = (f"{steps} frames x {len(bands)} bands of {bands[0][1]} rows ({sum(r for _, r in bands)}/{H} rows "
-              f"of each {W}x{H} frame), all {threads} host threads")
-    return mrays, dict(cores=threads, sample=sample, seconds=t_total, rays=rays,
+    n_timed = max(0, len(cam_list) - warm)
+    mrays = rays / t_total / 1e6 if t_total > 0 else 0.0
+    sample = (f"{n_timed} frames spread over the script x {len(bands)} bands of {bands[0][1]} rows "
+              f"({sum(r for _, r in bands)}/{H} rows of each {W}x{H} frame), {in_force} host threads"
+              f"{' (OpenMP, set by the arm itself)' if use_ref else ''}")
+    return mrays, dict(cores=in_force, sample=sample, seconds=t_total, rays=rays, frames=n_timed,
                        kind="reference" if use_ref else "port")
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm helpers
+# --------------------------------------------------------------------------------------------
+def timed_frames(ctx, traversal, cams, sched, warm_sched):
+    """Device time (ms) of len(sched) back-to-back launches, after the warm-up launches."""
+    for f in warm_sched:
+        ctx.render(traversal, cam_tuple(cams, f))
+    ctx.sync()
+    ctx.mark(0)
+    for f in sched:
+        ctx.render(traversal, cam_tuple(cams, f))
+    ctx.mark(1)
+    return ctx.mark_elapsed()
+
+
+def per_launch_ms(ctx, traversal, cams, sched):
+    out = []
+    for f in sched:
+        ctx.render(traversal, cam_tuple(cams, f))
+        out.append(ctx.sync())
+    return out
+
+
+def algorithmic_bytes(ctx, traversal, cams, sched, rays_per_frame, max_frames=12):
+    """Mean algorithmic bytes and steps per launch (instrumented STATS pass, untimed): 4 B per texel
+    fetch / node-field read as the shader source writes them + 4 B pixel store per ray."""
+    pick = sched[::max(1, len(sched) // max_frames)] or sched
+    tot_s = tot_b = 0
+    for f in pick:
+        _, _, (s, b) = ctx.stats_pass(traversal, cam_tuple(cams, f), per_ray=False)
+        tot_s += s
+        tot_b += b
+    return tot_b / len(pick) + 4.0 * rays_per_frame, tot_s / len(pick), len(pick)
+
+
+def roofline_block(workload, traversal, kernel_name, alg_bytes, alg_steps, n_stat, mean_ms, n_gpus):
+    peak, peak_kind = measured_peaks()
+    achieved = alg_bytes / (mean_ms / 1e3) / 1e9
+    prof = profile_entry(workload, kernel_name) if n_gpus == 1 else None
+    traffic = (int(prof["dram_bytes_read"]) + int(prof["dram_bytes_write"])) if prof else None
+    block = {
+        # which unit the committed ncu capture shows saturated: "hbm" (DRAM), "tex" (texture unit
+        # wavefronts), "issue" (warp instruction issue at the measured lanes per instruction)
+        "bound": (prof or {}).get("bound", "hbm"),
+        "kernel": kernel_name, "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind,
+        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+        "traffic_source": "profiles/traffic.json (ncu --set full capture of one camera frame)" if prof else None,
+        "algorithmic_bytes_per_launch": round(alg_bytes), "steps_per_launch": round(alg_steps),
+        "mean_kernel_ms": round(mean_ms, 5), "stat_frames": n_stat,
+        "note": "achieved = requested bytes (4 B per texel fetch / node-field read as the shader writes them + 4 B "
+                "per pixel) / kernel time; cache hits and fetches the skip table makes unnecessary mean the DRAM "
+                "traffic is far below it -- see dram_frac and the ncu evidence",
+    }
+    if prof:
+        for k in ("dram_frac_of_measured_peak", "issue_active", "lanes_per_instruction", "l2_hit", "capture_ms",
+                  "evidence"):
+            if k in prof:
+                block[k] = prof[k]
+        if traffic is not None and "capture_ms" in prof:
+            block["dram_frac"] = round(traffic / (prof["capture_ms"] / 1e3) / 1e9 / peak, 4)
+    return block
+
+
+def kernel_name_for(xb, ctx, traversal):
+    name = KERNEL_NAMES[traversal]
+    if traversal == "dda" and ctx.grid_layout()[0] == xb.LAYOUT_TEXTURE:
+        name = "dda_skip_tex_kernel" if os.environ.get("XN_DDA_SKIP", "1") != "0" else "dda_tex_kernel"
+    return name
+
+
+def measure_config(xb, ctx, name, traversal, frame, cams, steps, warmup, tree_side, dims):
+    """One per_config entry: device-timed Mrays/s over the spread schedule + its roofline block."""
+    W, H = frame
+    ctx.set_target((0, 0, W, H), (0, 0, W, H))
+    ctx.set_params((1, 1, 1), dims if traversal == "dda" else (tree_side,) * 3, EMISSION)
+    sched = frame_schedule(len(cams), steps)
+    warm = frame_schedule(len(cams), max(warmup, 3))
+    ms = timed_frames(ctx, traversal, cams, sched, warm)
+    kms = per_launch_ms(ctx, traversal, cams, sched)
+    alg_b, alg_s, n_stat = algorithmic_bytes(ctx, traversal, cams, sched, W * H)
+    value = W * H * len(sched) / (ms / 1e3) / 1e6
+    kname = kernel_name_for(xb, ctx, traversal)
+    return {
+        "workload": f"{name}: {WORKLOADS[name]['desc']}" if traversal == WORKLOADS[name]["traversal"]
+        else f"{name} volume, --shader {traversal}",
+        "traversal": traversal, "value": round(value, 2), "unit": "Mrays/s",
+        "ms_per_step": round(ms / len(sched), 5), "frames_per_s": round(len(sched) / (ms / 1e3), 2), "steps": len(sched),
+        "roofline": roofline_block(name, traversal, kname, alg_b, alg_s, n_stat, float(np.mean(kms)), 1),
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# shared page-locked host frames for the multi-GPU e2e path
+# --------------------------------------------------------------------------------------------
+class SharedHostFrames:
+    """`count` frames of w*h RGBA8 + a flag page in ONE POSIX shared-memory segment, mapped by every
+    rank and registered with CUDA (xn_host_register) so that device-to-host copies into it are
+    asynchronous.  flags[rank, slot] = sequence number of the last frame rank copied into slot."""
+
+    def __init__(self, xb, name, w, h, count, n_ranks, create):
+        from multiprocessing import shared_memory
+        self.frame_bytes = w * h * 4
+        self.flag_bytes = 4096
+        size = self.flag_bytes + count * self.frame_bytes
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size)
+        self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
+        self.base = self.buf.ctypes.data
+        xb.host_register(self.base, size)
+        self.xb = xb
+        self.flags = self.buf[:n_ranks * count * 4].view(np.uint32).reshape(n_ranks, count)
+        self.frames = [self.buf[self.flag_bytes + i * self.frame_bytes:self.flag_bytes + (i + 1) * self.frame_bytes]
+                       .reshape(h, w, 4) for i in range(count)]
+        self.create = create
+        if create:
+            self.flags[...] = 0
+
+    def frame_ptr(self, i):
+        return self.base + self.flag_bytes + i * self.frame_bytes
+
+    def flag_ptr(self, rank, slot):
+        return self.base + (rank * self.flags.shape[1] + slot) * 4
+
+    def close(self):
+        try:
+            self.xb.host_unregister(self.base)
+        except Exception:
+            pass
+        self.flags = self.frames = self.buf = None
+        try:
+            self.shm.close()
+            if self.create:
+                self.shm.unlink()
+        except Exception:
+            pass
 
 
 # --------------------------------------------------------------------------------------------
@@ -203,14 +388,15 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=150)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="xenodon_b200", choices=["xenodon_b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--traversal", default=None)
-    ap.add_argument("--gather", default="ipc", choices=["ipc", "nccl"])
-    ap.add_argument("--strong", action="store_true", help="keep the frame size fixed as N grows")
-    ap.add_argument("--no-extras", action="store_true", help="skip per-traversal extras and the CPU baseline")
+    ap.add_argument("--gather", default="host", choices=["host", "ipc", "nccl"])
+    ap.add_argument("--weak", action="store_true", help="grow the frame with N (rays per GPU fixed) instead of splitting one frame")
+    ap.add_argument("--strong", action="store_true", help="(default) keep the frame size fixed as N grows")
+    ap.add_argument("--no-extras", action="store_true", help="skip per_config, per-traversal extras and the CPU baseline")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,18 +409,18 @@ def main():
         log("bench.py --gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
         sys.exit(2)
 
-    wl = WORKLOADS[args.workload]
+    workload = args.workload or ("cfg4" if n_gpus == 1 else "cfg5")
+    wl = WORKLOADS[workload]
     traversal = args.traversal or wl["traversal"]
-    kind_name, nx, ny, nz = wl["volume"]
-    weak = not args.strong
+    weak = bool(args.weak) and not args.strong
     W, H = frame_for(wl["frame"], n_gpus, weak)
     cams = load_cameras(wl["camera"])
-    steps, warmup = args.steps, max(args.warmup, 0)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        run_reference_arm(args, wl, traversal, (W, H), cams, n_gpus)
+        run_reference_arm(args, workload, wl, traversal, (W, H), cams, n_gpus, weak)
         return
 
     import torch
@@ -245,45 +431,45 @@ def main():
     torch.cuda.set_device(local_rank)
     if n_gpus > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    kind_name, nx, ny, nz = wl["volume"]
     kind = xb.SYNTH_BUNNY if kind_name == "bunny" else xb.SYNTH_TNG
 
     ctx = xb.Context(local_rank)
     t_setup = time.perf_counter()
     ctx.synth_grid(kind, nx, ny, nz, SEED)  # generated directly in HBM
-    host_grid = None
     tree = None
-    need_tree = traversal != "dda"
-    extras = [] if args.no_extras or n_gpus > 1 or args.workload != "cfg2" else ["dda", "svo-rope", "svo-df", "svo-naive"]
     tree_side = None
-    want_host = (n_gpus == 1 and not args.no_extras and rank == 0)  # the CPU baseline needs host copies
-    if need_tree or extras:
-        rope = traversal == "svo-rope" or "svo-rope" in extras
+    extras = not args.no_extras and n_gpus == 1 and rank == 0
+    want_host_tree = extras and nx * ny * nz <= 1100 ** 3  # node array back on the host only for the CPU baseline
+    if traversal != "dda":
+        rope = traversal == "svo-rope"
         # `xenodon convert --chan-diff 0 [--rope]` on the GPU, from the resident grid (byte-identical
-        # to the host builder); the node array comes back to the host only for the CPU baseline
+        # to the host builder)
         tree, bstats, n_nodes, tree_side = ctx.convert_resident_grid(
-            chan_diff=0, type=xb.TYPE_ROPE if rope else xb.TYPE_SPARSE, bind=True, want_nodes=want_host)
+            chan_diff=0, type=xb.TYPE_ROPE if rope else xb.TYPE_SPARSE, bind=True, want_nodes=want_host_tree)
         if rank == 0:
             log(f"[bench] SVO (GPU convert --chan-diff 0{' --rope' if rope else ''}): {n_nodes} nodes, side "
-                f"{tree_side}, depth {bstats['depth']}, {n_nodes * 64 / 2**20:.0f} MiB resident")
+                f"{tree_side}, depth {bstats['depth']}")
     if rank == 0:
-        log(f"[bench] setup {time.perf_counter() - t_setup:.1f} s; frame {W}x{H}, traversal {traversal}, N={n_gpus}")
+        log(f"[bench] {workload}: setup {time.perf_counter() - t_setup:.1f} s; frame {W}x{H}, traversal {traversal}, N={n_gpus}")
 
     grid_layout = {xb.LAYOUT_LINEAR: "x-major linear", xb.LAYOUT_BRICKED: "8x8x8 bricks, Morton inside",
                    xb.LAYOUT_TEXTURE: "3-D CUDA array (block-linear), texture units"}.get(
         ctx.grid_layout()[0], "none")
     display = (0, 0, W, H)
     ctx.set_params((1, 1, 1), (nx, ny, nz) if traversal == "dda" else (tree_side,) * 3, EMISSION)
+    sched = frame_schedule(len(cams), steps)
+    warm_sched = frame_schedule(len(cams), warmup)
 
     # ---- partition + gather plumbing ----
-    frame_ptr = None
     band = None
-    if n_gpus == 1:
-        ctx.set_target(display, display)
-    elif args.gather == "ipc":
-        # every rank shades its stripes of the full frame and stores them into rank 0's frame
-        ctx.set_target(display, display)
+    frame_ptrs = None
+    gather = args.gather if n_gpus > 1 else "single"
+    ctx.set_target(display, display)
+    if n_gpus > 1 and gather in ("host", "ipc"):
+        # every rank shades its 16-row stripes of the full frame; in the kernel-timed region the
+        # stripes are stored straight into rank 0's frame over NVLink
         ctx.set_interleave(n_gpus, rank)
-        # two frames: while rank 0 copies frame i to the host, frame i+1 is stored into the other
         if rank == 0:
             made = [ctx.frame_buffer_create(W, H) for _ in range(2)]
             frame_ptrs = [m[0] for m in made]
@@ -293,9 +479,8 @@ def main():
         dist.broadcast_object_list(obj, src=0)
         if rank != 0:
             frame_ptrs = [ctx.frame_buffer_open(h) for h in obj[0]]
-        frame_ptr = frame_ptrs[0]
-        ctx.set_target_buffer(frame_ptr, W)
-    else:
+        ctx.set_target_buffer(frame_ptrs[0], W)
+    elif n_gpus > 1:
         from xenodon_b200 import distributed as xd
         rows = xd.band_rows(H, n_gpus)
         band = (0, rows[rank], W, rows[rank + 1] - rows[rank])
@@ -307,22 +492,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather_nccl():
-        """NCCL gather of contiguous bands to rank 0 (the plain-library baseline of the gather)."""
+    tile = None
+    gathered = None
+    if gather == "nccl":
         tile = torch.empty((band[3], W), dtype=torch.int32, device="cuda")
         ctx.set_target_buffer(tile.data_ptr(), W)
-        return tile
-
-    tile = gather_nccl() if (n_gpus > 1 and args.gather == "nccl") else None
-    gathered = None
-    if tile is not None and rank == 0:
-        sizes = [rows[r + 1] - rows[r] for r in range(n_gpus)]
-        gathered = [torch.empty((s, W), dtype=torch.int32, device="cuda") for s in sizes]
+        if rank == 0:
+            sizes = [rows[r + 1] - rows[r] for r in range(n_gpus)]
+            gathered = [torch.empty((s, W), dtype=torch.int32, device="cuda") for s in sizes]
 
     def do_gather():
+        """NCCL gather of contiguous bands to rank 0 (the plain-library baseline of the gather)."""
         if tile is None:
             return
-        # bands have different heights: point-to-point (grouped) instead of dist.gather
         if rank == 0:
             reqs = [dist.irecv(gathered[r], src=r) for r in range(1, n_gpus)]
             gathered[0].copy_(tile)
@@ -331,18 +513,17 @@ def main():
         else:
             dist.send(tile, dst=0)
 
-    # ---- kernel-only timed region ----
-    for i in range(warmup):
-        ctx.render(traversal, cam_tuple(cams, i))
+    # ---- kernel-timed region: K frames back to back, finished pixels land in rank 0's HBM ----
+    for f in warm_sched:
+        ctx.render(traversal, cam_tuple(cams, f))
         ctx.sync()
         do_gather()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count()
-    kernel_ms = []
     ctx.mark(0)
-    for i in range(steps):
-        ctx.render(traversal, cam_tuple(cams, warmup + i))
+    for f in sched:
+        ctx.render(traversal, cam_tuple(cams, f))
         if tile is not None:
             ctx.sync()
             do_gather()
@@ -352,29 +533,89 @@ def main():
     launches = ctx.launch_count() - launches0
 
     # per-frame kernel durations (CUDA events on the launching stream), for the roofline
-    for i in range(steps):
-        ctx.render(traversal, cam_tuple(cams, warmup + i))
-        kernel_ms.append(ctx.sync())
+    kernel_ms = per_launch_ms(ctx, traversal, cams, sched)
     barrier()
 
-    # ---- end-to-end region: camera from the host every step, frame back to pinned host memory ----
-    pinned = [xb.PinnedFrame(W, H), xb.PinnedFrame(W, H)] if rank == 0 else None
+    # ---- end-to-end region: camera from the host every step, every frame delivered to page-locked host memory ----
     e2e_d2h = W * H * 4
-    for i in range(min(warmup, 3)):
-        if n_gpus == 1:
-            ctx.render_download_async(traversal, cam_tuple(cams, i), pinned[i & 1])
-            ctx.sync()
-    barrier()
-    t0 = time.perf_counter()
+    shared = None
+    pinned = None
+    e2e_info = {}
     if n_gpus == 1:
-        for i in range(steps):
-            ctx.render_download_async(traversal, cam_tuple(cams, warmup + i), pinned[i & 1])
+        pinned = [xb.PinnedFrame(W, H), xb.PinnedFrame(W, H)]
+        for j, f in enumerate(warm_sched[:3]):
+            ctx.render_download_async(traversal, cam_tuple(cams, f), pinned[j & 1])
         ctx.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for i, f in enumerate(sched):
+            ctx.render_download_async(traversal, cam_tuple(cams, f), pinned[i & 1])
+        ctx.sync()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        last_frame = pinned[(steps - 1) & 1].array
+        e2e_info["path"] = "xn_render_download_async: two alternating device targets, copy-out of frame i overlaps frame i+1"
+    elif gather == "host":
+        # every rank copies its own stripes into the shared page-locked frame (N PCIe links);
+        # a stream-ordered flag per rank and slot says "frame seq is complete in this slot"
+        ctx.set_target_buffer(None, 0)
+        SLOTS = 2
+        name = [f"xn_bench_{os.getpid()}_{int(time.time())}" if rank == 0 else None]
+        dist.broadcast_object_list(name, src=0)
+        if rank == 0:
+            shared = SharedHostFrames(xb, name[0], W, H, SLOTS, n_gpus, create=True)
+        dist.barrier()
+        if rank != 0:
+            shared = SharedHostFrames(xb, name[0], W, H, SLOTS, n_gpus, create=False)
+        dist.barrier()
+        ack = shared.buf[2048:2052].view(np.uint32)  # frames rank 0 has seen complete (consumer side)
+
+        def produce(seq, f):
+            slot = seq % SLOTS
+            # the consumer must have released this slot (frame seq - SLOTS) before it is overwritten
+            while seq > SLOTS and int(ack[0]) < seq - SLOTS:
+                pass
+            ctx.render_download_to(traversal, cam_tuple(cams, f), shared.frame_ptr(slot), W)
+            ctx.signal_after_copy(shared.flag_ptr(rank, slot), seq)
+
+        def consume(seq):
+            slot = seq % SLOTS
+            fl = shared.flags[:, slot]
+            while int(fl.min()) < seq:
+                pass
+            ack[0] = seq  # a consumer (PNG writer, display) would use shared.frames[slot] here
+
+        base = 0
+        for j, f in enumerate(warm_sched[:3]):
+            base += 1
+            produce(base, f)
+            if rank == 0:
+                consume(base)
+        ctx.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for i, f in enumerate(sched):
+            produce(base + 1 + i, f)
+            if rank == 0 and i >= 1:
+                consume(base + i)  # one frame behind: frame i renders while frame i-1 completes
+        if rank == 0:
+            consume(base + steps)
+        ctx.sync()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        last_frame = shared.frames[(base + steps) % SLOTS] if rank == 0 else None
+        e2e_info["path"] = (f"each rank copies its own 16-row stripes into one page-locked host frame shared by the {n_gpus} "
+                            "processes (POSIX shm + cudaHostRegister): the frame leaves over N PCIe links; per-rank "
+                            "stream-ordered completion flags, no collective or host sync inside the loop")
+        e2e_info["nvlink_bytes_per_step"] = 0
     else:
+        pinned = [xb.PinnedFrame(W, H), xb.PinnedFrame(W, H)] if rank == 0 else None
         if tile is None:
             ctx.set_target_buffer(frame_ptrs[0], W)
-        for i in range(steps):
-            ctx.render(traversal, cam_tuple(cams, warmup + i))
+        barrier()
+        t0 = time.perf_counter()
+        for i, f in enumerate(sched):
+            ctx.render(traversal, cam_tuple(cams, f))
             ctx.sync()
             if tile is not None:
                 do_gather()
@@ -395,14 +636,34 @@ def main():
                     ctx.set_target_buffer(frame_ptrs[(i + 1) & 1], W)
         if rank == 0 and tile is None:
             ctx.copy_sync()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    last_frame = pinned[(steps - 1) & 1].array.copy() if rank == 0 else None
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        last_frame = pinned[(steps - 1) & 1].array if rank == 0 else None
+        e2e_info["path"] = ("kernel-epilogue peer stores into rank 0's frame over NVLink, then rank 0 copies the whole frame "
+                            "over its one PCIe link" if gather == "ipc" else "NCCL send/recv of bands to rank 0, then one PCIe link")
+        e2e_info["nvlink_bytes_per_step"] = int(W * H * 4 * (n_gpus - 1) / n_gpus)
+    if last_frame is not None:
+        last_frame = np.array(last_frame, copy=True)
 
     clocks = sampler.stop() if sampler else None
 
+    # ---- the same workload on ONE GPU, measured by rank 0 alone (so a scaling curve can be read off one run) ----
+    single = None
+    if n_gpus > 1 and gather in ("host", "ipc") and not weak:
+        if rank == 0:
+            ctx.set_interleave(1, 0)
+            ctx.set_target_buffer(None, 0)
+            k = max(3, min(steps, 10))
+            s1 = frame_schedule(len(cams), k)
+            ms1 = timed_frames(ctx, traversal, cams, s1, s1[:2])
+            single = {"value": round(W * H * k / (ms1 / 1e3) / 1e6, 2), "unit": "Mrays/s", "steps": k,
+                      "note": "same frame, same volume, one GPU (rank 0 alone, device-timed)"}
+            ctx.set_interleave(n_gpus, rank)
+        barrier()
+
     # ---- reduce over ranks: max time, sum rays ----
     region_all, e2e_all, rays_all = region_ms, e2e_s, my_rays
+    kernel_ms_all = [float(np.mean(kernel_ms))]
     if n_gpus > 1:
         t = torch.tensor([region_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -410,20 +671,20 @@ def main():
         r = torch.tensor([my_rays], dtype=torch.int64, device="cuda")
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
         rays_all = int(r.item())
+        km = torch.zeros(n_gpus, dtype=torch.float64, device="cuda")
+        km[rank] = float(np.mean(kernel_ms))
+        dist.all_reduce(km, op=dist.ReduceOp.SUM)
+        kernel_ms_all = km.tolist()
 
     # ---- algorithmic bytes (instrumented pass, untimed) for the roofline of the dominant kernel ----
-    alg_bytes = 0
-    alg_steps = 0
-    stat_frames = list(range(0, steps, max(1, steps // 30)))  # every ~5th frame; scaled to all frames
-    for i in stat_frames:
-        _, _, (s, b) = ctx.stats_pass(traversal, cam_tuple(cams, warmup + i), per_ray=False)
-        alg_steps += s
-        alg_bytes += b
-    scale = steps / len(stat_frames)
-    alg_bytes_per_frame = (alg_bytes * scale + my_rays * 4.0 * steps) / steps  # + 4 B pixel store per ray
-    alg_steps_per_frame = alg_steps * scale / steps
+    if n_gpus > 1 and gather != "nccl":
+        ctx.set_target_buffer(None, 0)
+    alg_bytes, alg_steps, n_stat = algorithmic_bytes(ctx, traversal, cams, sched, my_rays)
 
     if rank != 0:
+        if shared:
+            dist.barrier()
+            shared.close()
         if n_gpus > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -431,139 +692,184 @@ def main():
 
     value = rays_all * steps / (region_all / 1e3) / 1e6
     e2e_value = rays_all * steps / e2e_all / 1e6
-    peak, peak_kind = measured_peaks()
     mean_kernel_ms = float(np.mean(kernel_ms))
-    achieved = alg_bytes_per_frame / (mean_kernel_ms / 1e3) / 1e9
-    kernel_name = {"dda": "dda_kernel", "esvo": "esvo_kernel", "svo-rope": "svo_rope_kernel",
-                   "svo-df": "svo_df_kernel", "svo-naive": "svo_naive_kernel"}[traversal]
-    if traversal == "dda" and ctx.grid_layout()[0] == xb.LAYOUT_TEXTURE:
-        kernel_name = "dda_tex_kernel"
+    kernel_name = kernel_name_for(xb, ctx, traversal)
+    e2e = {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 36 * n_gpus,
+           "d2h_bytes_per_step": e2e_d2h, "frames_per_s": round(steps / e2e_all, 2),
+           "d2h_gb_per_s": round(e2e_d2h * steps / e2e_all / 1e9, 2)}
+    e2e.update(e2e_info)
     result = {
         "metric": "Mrays/s", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": n_gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": round(region_all / steps, 5), "higher_is_better": True,
         "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_s": round(steps / (region_all / 1e3), 2),
         "config": {
-            "workload": f"{args.workload}: {wl['desc']}", "traversal": traversal, "frame": f"{W}x{H}",
+            "workload": f"{workload}: {wl['desc']}", "traversal": traversal, "frame": f"{W}x{H}",
             "volume": f"{kind_name} {nx}x{ny}x{nz} seed {SEED}", "camera": wl["camera"], "emission": EMISSION,
+            "frames": f"{steps} steps = script frames floor(i*{len(cams)}/{steps}) (whole path: exterior, fly-over, interior)",
             "grid_layout": grid_layout if traversal == "dda" else None,
             "partition": ("single region" if n_gpus == 1 else
-                          f"16-row stripes round-robin over {n_gpus} GPUs, peer stores into rank 0's frame (CUDA IPC/NVLink)"
-                          if args.gather == "ipc" else f"{n_gpus} horizontal bands, NCCL send/recv gather to rank 0"),
+                          f"16-row stripes round-robin over {n_gpus} GPUs, volume replicated; kernel-timed region: peer stores into "
+                          f"rank 0's frame (CUDA IPC / NVLink); e2e: --gather {gather}"
+                          if gather != "nccl" else f"{n_gpus} horizontal bands, NCCL send/recv gather to rank 0"),
             "l2": "inputs larger than L2 (volume resident in HBM exceeds 126 MB); camera changes every step",
         },
-        "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 36 * n_gpus,
-                "d2h_bytes_per_step": e2e_d2h, "frames_per_s": round(steps / e2e_all, 2)},
+        "e2e": e2e,
         "gpu_launches": int(launches) * n_gpus,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 1), "peak": peak,
-                     "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": measured_traffic(args.workload, kernel_name) if n_gpus == 1 else None,
-                     "traffic_source": "profiles/traffic.json (ncu --set full capture of one camera frame)",
-                     "algorithmic_bytes_per_launch": round(alg_bytes_per_frame),
-                     "steps_per_launch": round(alg_steps_per_frame),
-                     "mean_kernel_ms": round(mean_kernel_ms, 5),
-                     "note": "requested bytes (4 B per texel fetch / node-field read as the shader writes them "
-                             "+ 4 B per pixel); cache hits make this exceed DRAM traffic"},
-        "reference_stats": {"mray/s (rays / summed device ms)": round(
-            rays_all * steps / n_gpus / (sum(kernel_ms)) / 1e3, 2)},
+        "roofline": roofline_block(workload, traversal, kernel_name, alg_bytes, alg_steps, n_stat, mean_kernel_ms, n_gpus),
+        "reference_stats": {"mray/s (rays / summed device ms, RenderStats.cpp:22-24)": round(
+            rays_all / (sum(kernel_ms_all) * 1000.0), 2)},
     }
+    if single:
+        result["single_gpu_same_workload"] = single
 
-    # ---- extras on the same volume (N=1, cfg2 only): every traversal, same frames ----
-    per_traversal = {traversal: round(value, 2)}
-    for t in extras:
-        if t == traversal:
-            continue
-        ctx.set_params((1, 1, 1), (nx, ny, nz) if t == "dda" else (tree_side,) * 3, EMISSION)
-        for i in range(3):
-            ctx.render(t, cam_tuple(cams, i))
-        ctx.sync()
-        ctx.mark(0)
-        for i in range(steps):
-            ctx.render(t, cam_tuple(cams, warmup + i))
-        ctx.mark(1)
-        ms = ctx.mark_elapsed()
-        per_traversal[t] = round(W * H * steps / (ms / 1e3) / 1e6, 2)
-    if len(per_traversal) > 1:
-        result["per_traversal_mrays_s"] = per_traversal
+    if extras:
+        try:
+            result["per_config"] = per_config_block(xb, ctx, workload, traversal, result, steps, warmup, local_rank)
+        except Exception as e:  # extras must never take the headline down with them
+            result["per_config"] = {"error": str(e)}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample ----
-    if n_gpus == 1 and not args.no_extras:
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
+    if extras:
         try:
             if traversal == "dda":
-                if nx * ny * nz * 4 > (8 << 30):
-                    raise RuntimeError("volume too large for the host-side baseline sample")
-                host_grid = ctx.download_grid()
+                host_grid = ctx.download_grid().data  # the resident voxels themselves
             else:
-                host_grid = xb.Grid(np.zeros((1, 1, 1, 4), np.uint8))  # unused by the octree traversals
-            sample_steps = max(1, min(steps, 12))
-            sub = cams[np.linspace(0, len(cams) - 1, sample_steps).astype(int)] if len(cams) > 1 else cams
-            mr, info = run_oracle_frames(args.workload, traversal, (W, H), sub, sample_steps, 1,
-                                         host_grid.data, tree)
+                host_grid = np.zeros((1, 1, 1, 4), np.uint8)  # unused by the octree traversals
+                if tree is None:
+                    raise RuntimeError("node array of this volume is not brought back to the host")
+            k = max(2, min(steps, 6))
+            sub = [cam_tuple(cams, f) for f in frame_schedule(len(cams), k)]
+            bands = oracle_sample_rows(H, bands=8, rows_per_band=4 if W * H > 4_000_000 else 8)
+            mr, info = run_oracle_frames(traversal, (W, H), sub[:1] + sub, host_grid, tree, bands=bands)
             result["cpu_baseline"] = {"value": round(mr, 3), "unit": "Mrays/s", "cores": info["cores"],
-                                      "kind": info["kind"], "sample": info["sample"]}
+                                      "kind": info["kind"], "sample": info["sample"],
+                                      "seconds": round(info["seconds"], 2)}
             # parity spot check of the last e2e frame against the oracle (not timed)
             from oracle import xo
-            cam = cam_tuple(cams, warmup + steps - 1)
+            cam = cam_tuple(cams, sched[-1])
             y0 = H // 2 - 8
-            kw = dict(camera=cam, output=(0, y0, W, 16), display=display, emission=EMISSION, want_stats=False)
-            ref = (xo.render("dda", grid=host_grid.data, **kw) if traversal == "dda"
+            kw = dict(camera=cam, output=(0, y0, W, 16), display=display, emission=EMISSION, want_stats=False,
+                      threads=host_threads())
+            ref = (xo.render("dda", grid=host_grid, **kw) if traversal == "dda"
                    else xo.render(traversal, nodes=tree.nodes, side=tree.side, **kw))[0]
             d = np.abs(ref.astype(int) - last_frame[y0:y0 + 16].astype(int)).max(axis=-1)
-            result["parity_check"] = {"rows": 16, "within_1_of_255": float((d <= 1).mean()), "max_diff": int(d.max())}
+            result["parity_check"] = {"rows": 16, "frame": int(sched[-1]), "within_1_of_255": float((d <= 1).mean()),
+                                      "max_diff": int(d.max())}
         except Exception as e:  # the baseline must never take the GPU number down with it
             result["cpu_baseline"] = {"error": str(e)}
 
     print(json.dumps(result), file=_JSON_OUT, flush=True)
+    if shared:
+        dist.barrier()
+        shared.close()
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def run_reference_arm(args, wl, traversal, frame, cams, n_gpus):
-    """--impl reference: the reference's CPU-runnable stand-in (the oracle port) on the host cores.
-    The volume comes from the host generator (bit-identical to the device generator)."""
-    import xenodon_b200 as xb  # host-side formats / generators only; no GPU call on this arm
+def per_config_block(xb, ctx, workload, traversal, headline, steps, warmup, device):
+    """The other BASELINE configurations measured the same way (device-timed, whole camera path) in
+    the same process; the headline's own entry is copied in.  Volumes are generated in HBM, octrees
+    built on the GPU from the resident grid."""
+    out = {}
+    head = {"workload": headline["config"]["workload"], "traversal": traversal, "value": headline["value"],
+            "unit": "Mrays/s", "ms_per_step": headline["ms_per_step"], "frames_per_s": headline["frames_per_s"],
+            "steps": steps, "roofline": headline["roofline"]}
+    out[workload if traversal == WORKLOADS[workload]["traversal"] else f"{workload}:{traversal}"] = head
+    plan = [  # (volume key, [(config name, traversal)])
+        (("tng", 2048, 2048, 2048), [("cfg4", "dda"), ("cfg4e", "esvo")]),
+        (("tng", 1024, 1024, 1024), [("cfg3", "dda"), ("cfg3r", "svo-rope")]),
+        (("bunny", 512, 361, 512), [("cfg1", "dda"), ("cfg2", "esvo"), ("cfg2", "svo-rope"), ("cfg2", "svo-df"),
+                                    ("cfg2", "svo-naive"), ("cfg2", "dda")]),
+    ]
+    cur_volume = WORKLOADS[workload]["volume"]
+    cur_tree = {"esvo": "sparse", "svo-df": "sparse", "svo-naive": "sparse", "svo-rope": "rope"}.get(traversal)
+    for vol, entries in plan:
+        todo = [(n, t) for n, t in entries
+                if (n if t == WORKLOADS[n]["traversal"] else f"{n}:{t}") not in out]
+        if not todo:
+            continue
+        if vol != cur_volume:
+            kind_name, nx, ny, nz = vol
+            ctx.synth_grid(xb.SYNTH_BUNNY if kind_name == "bunny" else xb.SYNTH_TNG, nx, ny, nz, SEED)
+            cur_volume, cur_tree = vol, None
+        dims = vol[1:]
+        side = None
+        # the rope tree serves every octree traversal (ropes live in leaf records the others never read)
+        need_rope = any(t == "svo-rope" for _, t in todo)
+        for name, t in sorted(todo, key=lambda e: e[1] != "dda"):
+            if t != "dda":
+                want = "rope" if need_rope else "sparse"
+                if cur_tree != want and not (cur_tree == "rope" and want == "sparse"):
+                    _, _, _, side = ctx.convert_resident_grid(
+                        chan_diff=0, type=xb.TYPE_ROPE if want == "rope" else xb.TYPE_SPARSE, bind=True, want_nodes=False)
+                    cur_tree = want
+                elif side is None:
+                    side = 1 << int(np.ceil(np.log2(max(dims))))
+            cams = load_cameras(WORKLOADS[name]["camera"])
+            key = name if t == WORKLOADS[name]["traversal"] else f"{name}:{t}"
+            t0 = time.perf_counter()
+            out[key] = measure_config(xb, ctx, name, t, WORKLOADS[name]["frame"], cams, steps, warmup, side, dims)
+            log(f"[bench] per_config {key}: {out[key]['value']} Mrays/s ({time.perf_counter() - t0:.1f} s)")
+    return out
+
+
+def run_reference_arm(args, workload, wl, traversal, frame, cams, n_gpus, weak):
+    """--impl reference: the reference's compute-shader text compiled as C++ (oracle/_ref, OpenMP) on
+    the host cores, or the C restatement where that library is absent.  No GPU call on this arm: the
+    volume comes from the host generator (bit-identical to the device generator)."""
+    import xenodon_b200 as xb  # host-side formats / generators only
     kind_name, nx, ny, nz = wl["volume"]
     W, H = frame
-    steps, warmup = args.steps, max(args.warmup, 0)
-    if nx * ny * nz > 1100 ** 3:
-        print(json.dumps({"impl": "reference", "unavailable": "host copy of this volume exceeds the arm's budget"}),
-              file=_JSON_OUT, flush=True)
-        return
-    log(f"[reference arm] generating {kind_name} {nx}x{ny}x{nz} on the host ...")
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    threads = host_threads()
+    t0 = time.perf_counter()
+    log(f"[reference arm] generating {kind_name} {nx}x{ny}x{nz} on the host ({nx * ny * nz * 4 / 2**30:.1f} GiB) ...")
     grid = xb.Grid.synthetic(xb.SYNTH_BUNNY if kind_name == "bunny" else xb.SYNTH_TNG, nx, ny, nz, SEED)
+    t_gen = time.perf_counter() - t0
     tree = None
     if traversal != "dda":
         log("[reference arm] convert --chan-diff 0 ...")
         tree, _ = xb.build_octree(grid, chan_diff=0, type=xb.TYPE_ROPE if traversal == "svo-rope" else xb.TYPE_SPARSE)
-    # bounded: at most ~40 sampled frames spread over the requested steps
-    n = max(1, min(steps, 40))
-    idx = np.linspace(warmup, warmup + steps - 1, n).astype(int)
-    sub = cams[[i % len(cams) for i in idx]]
-    t0 = time.perf_counter()
-    mr, info = run_oracle_frames(args.workload, traversal, (W, H), sub, n, min(warmup, 1), grid.data, tree,
-                                 prefer_ref=True)
-    wall = time.perf_counter() - t0
-    rows = sum(r for _, r in oracle_sample_rows(H))
+    # a step of this arm = a bounded row sample of one frame; the frames are the GPU arm's schedule
+    # (thinned to at most 24 so the arm ends within minutes on the big volumes)
+    sched = frame_schedule(len(cams), steps)
+    n = max(1, min(steps, 24))
+    pick = [sched[(i * len(sched)) // n] for i in range(n)]
+    rows_per_band = 8 if W * H <= 4_000_000 else 4
+    bands = oracle_sample_rows(H, bands=8, rows_per_band=rows_per_band)
+    cam_list = [cam_tuple(cams, f) for f in pick]
+    warm = min(max(warmup, 0), 1)
+    t1 = time.perf_counter()
+    mr, info = run_oracle_frames(traversal, (W, H), cam_list[:warm] + cam_list, grid.data, tree, prefer_ref=True,
+                                 warm=warm, bands=bands)
+    wall = time.perf_counter() - t1
+    rows = sum(r for _, r in bands)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": round(mr, 3), "unit": "Mrays/s", "n_gpus": n_gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": round(info["seconds"] / n * 1e3 * (H / rows), 3),
-        "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+        "steps": steps, "warmup": warmup,
+        "ms_per_step": round(info["seconds"] / max(info["frames"], 1) * 1e3 * (H / rows), 3),
+        "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "traversal": traversal, "frame": f"{W}x{H}",
+        "config": {"workload": f"{workload}: {wl['desc']}", "traversal": traversal, "frame": f"{W}x{H}",
                    "volume": f"{kind_name} {nx}x{ny}x{nz} seed {SEED}", "camera": wl["camera"],
                    "emission": EMISSION,
+                   "frames": f"{info['frames']} of the GPU arm's {steps} script frames floor(i*{len(cams)}/{steps})",
                    "note": "the reference's Vulkan build cannot run in this image (no loader/ICD/glslc); this arm "
                            "times its compute-shader text compiled as C++ (oracle/_ref, kind 'reference') or, where "
-                           "that library is absent, the C restatement oracle/xn_oracle.c (kind 'port')"},
+                           "that library is absent, the C restatement oracle/xn_oracle.c (kind 'port'); ms_per_step is "
+                           "the sampled rows scaled to a whole frame"},
         "cpu_baseline": {"value": round(mr, 3), "unit": "Mrays/s", "cores": info["cores"], "kind": info["kind"],
-                         "sample": info["sample"]},
+                         "sample": info["sample"], "host_threads_available": threads,
+                         "omp_num_threads_env_at_launch": os.environ.get("XN_LAUNCH_OMP", None)},
         "e2e": {"value": round(mr, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": round(wall, 1),
+        "gpu_launches": 0, "wall_s": round(wall, 1), "volume_generation_s": round(t_gen, 1),
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":
+    os.environ.setdefault("XN_LAUNCH_OMP", os.environ.get("OMP_NUM_THREADS", "unset"))
     main()

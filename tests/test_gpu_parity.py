@@ -272,6 +272,63 @@ def test_dda_resident_layouts_match_oracle(xb, xo, cam, dims, layout):
             assert image_diff(img, ref)[0] <= 1
 
 
+def _skip_volume(xb, name, rng):
+    if name == "blobs":  # large uniform blobs in a black box, ragged dimensions (partial edge bricks)
+        return blobby_grid(rng, 70, 45, 61)
+    if name == "tng":  # the benchmark's gas volume: ~90 % floor colour (0, 0, 3)
+        return xb.Grid.synthetic(xb.SYNTH_TNG, 96, 80, 130, seed=1729).data
+    if name == "bunny":
+        return xb.Grid.synthetic(xb.SYNTH_BUNNY, 64, 45, 64, seed=1729).data
+    if name == "one_colour":  # no mixed brick at all; the edge bricks of the ragged axes are mixed with border black
+        g = np.zeros((37, 64, 50, 4), np.uint8)
+        g[...] = (7, 200, 31, 255)
+        return g
+    if name == "alpha_only":  # rgb uniform, alpha varies: the march reads rgb only (dda.comp:45-46)
+        g = np.zeros((32, 32, 32, 4), np.uint8)
+        g[..., :3] = (90, 3, 250)
+        g[..., 3] = rng.integers(0, 256, (32, 32, 32), dtype=np.uint8)
+        return g
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("shift", [2, 3, 4])
+@pytest.mark.parametrize("volume", ["blobs", "tng", "bunny", "one_colour", "alpha_only"])
+def test_dda_skip_table_leaves_images_and_steps_unchanged(xb, xo, volume, shift, monkeypatch):
+    """The texture-residency DDA consults the skip table (uniform bricks and how far their colour
+    extends) instead of fetching texels it can know: every ray must still take exactly the
+    reference's steps (per-ray step / byte counts equal the oracle's), the strict image must be
+    bit-identical and the fast image within 1/255, for every brick size, for cameras outside,
+    inside and axis-aligned, and with the table switched off."""
+    rng = np.random.default_rng(shift * 131 + len(volume))
+    g = _skip_volume(xb, volume, rng)
+    out = (0, 0, 192, 108)
+    for cam in ("orbit", "inside", "oblique", "axis_neg", "single"):
+        ref, rsteps, rbytes = xo.render("dda", grid=g, camera=CAMERAS[cam], output=out, emission=3.0)
+        for skip in (("1", "0") if shift == 3 else ("1",)):  # the table-less kernel ignores the brick size
+            monkeypatch.setenv("XN_DDA_SKIP", skip)
+            monkeypatch.setenv("XN_SKIP_SHIFT", str(shift))
+            for strict in (True, False):
+                ctx = xb.Context(0)
+                try:
+                    ctx.set_precision(strict)
+                    ctx.set_grid_layout(xb.LAYOUT_TEXTURE)
+                    ctx.upload_grid(xb.Grid(g))
+                    ctx.set_target(out)
+                    ctx.set_params((1, 1, 1), None, 3.0)
+                    ctx.render("dda", CAMERAS[cam])
+                    ctx.sync()
+                    img = ctx.download()
+                    steps, nbytes, _ = ctx.stats_pass("dda", CAMERAS[cam])
+                finally:
+                    ctx.close()
+                tag = (volume, shift, cam, skip, strict)
+                assert np.array_equal(steps, rsteps) and np.array_equal(nbytes, rbytes), tag
+                if strict:
+                    assert np.array_equal(img, ref), tag
+                else:
+                    assert image_diff(img, ref)[0] <= 1, tag
+
+
 def test_dda_bricked_gpu_convert_and_auto_policy(xb):
     """GPU convert reads the grid through the linear view whatever is resident; AUTO keeps small
     grids linear and XN_BRICK_MIN_VOXELS moves the threshold."""

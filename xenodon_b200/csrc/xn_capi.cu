@@ -107,6 +107,8 @@ struct xn_ctx {
     uint64_t node_count = 0, internal_count = 0, side = 0;
     uint32_t root_meta = 0, max_depth = 0;
     bool grid_has_black_background = false;
+    uint4* skip_table = nullptr; // DDA skip table of the resident grid (any layout)
+    uint32_t skip_dim[3] = {0, 0, 0}, skip_shift = 0;
 
     // target
     xn_rect output{0, 0, 0, 0}, display{0, 0, 0, 0};
@@ -138,6 +140,8 @@ struct xn_ctx {
         if (grid) cudaFree(grid);
         if (bricks) cudaFree(bricks);
         free_texture();
+        if (skip_table) cudaFree(skip_table);
+        skip_table = nullptr;
         grid = bricks = nullptr;
         nx = ny = nz = 0;
     }
@@ -210,6 +214,9 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     }
     p.tex_unorm = ctx->tex_unorm;
     p.tex_raw = ctx->tex_raw;
+    p.skip_table = ctx->skip_table;
+    for (int i = 0; i < 3; ++i) p.skip_dim[i] = ctx->skip_dim[i];
+    p.skip_shift = ctx->skip_shift;
     p.nx = (uint32_t)ctx->nx;
     p.ny = (uint32_t)ctx->ny;
     p.nz = (uint32_t)ctx->nz;
@@ -237,6 +244,27 @@ void classify_grid(xn_ctx* ctx) {
     cudaFree(d);
     if (e != cudaSuccess) throw CudaError{e, "classify_grid"};
     ctx->grid_has_black_background = h[1] > 0 && h[0] * 4 >= h[1];
+
+    // DDA skip table (uniform bricks + how far their colour extends), from the linear copy that
+    // every upload path produces first.  XN_DDA_SKIP=0 leaves it out (A/B runs);
+    // XN_SKIP_SHIFT = log2 of the brick edge (default 3), XN_SKIP_CAP = largest radius in bricks.
+    if (ctx->skip_table) cudaFree(ctx->skip_table);
+    ctx->skip_table = nullptr;
+    const char* on = std::getenv("XN_DDA_SKIP");
+    if (on && on[0] == '0') return;
+    uint32_t shift = 3, cap = 32;
+    if (const char* s = std::getenv("XN_SKIP_SHIFT")) shift = (uint32_t)std::strtoul(s, nullptr, 10);
+    if (const char* s = std::getenv("XN_SKIP_CAP")) cap = (uint32_t)std::strtoul(s, nullptr, 10);
+    if (ctx->nx > 0x7FFFFFu || ctx->ny > 0x7FFFFFu || ctx->nz > 0x7FFFFFu) return; // texel centres exact below 2^23
+    e = xn::build_skip_table(ctx->grid, (uint32_t)ctx->nx, (uint32_t)ctx->ny, (uint32_t)ctx->nz, shift, cap,
+                             &ctx->skip_table, ctx->skip_dim, ctx->stream);
+    if (e != cudaSuccess) {
+        // the table only saves fetches: without it the march reads every texel
+        cudaGetLastError();
+        ctx->skip_table = nullptr;
+        return;
+    }
+    ctx->skip_shift = shift;
 }
 
 // ---- resident layout of the grid (xn_brick.h) ----
@@ -502,7 +530,6 @@ int xn_ctx_create(int cuda_device, xn_ctx** out) {
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
         }
-        XN_CUDA(xn::configure_kernels());
         *out = ctx.release();
     });
 }

@@ -77,6 +77,12 @@ struct FrameParams {
     // texture residency: the grid as a 3-D CUDA array (block-linear tiling, border = 0) seen through
     // two texture objects: channels as c / 255 floats (fast mode) and as raw bytes (strict mode)
     unsigned long long tex_unorm, tex_raw;
+    // DDA skip table (built at upload, xn_util_kernels.cu): one 16-byte entry per 2^skip_shift-voxel
+    // brick = { rgb | uniform << 24, 0, radii of octants 0-3, radii of octants 4-7 }: from a uniform
+    // brick, the k^3 bricks in the direction of travel hold this colour; extent skip_dim[] bricks
+    // including a one-brick border of border colour.  nullptr = no table (every texel is fetched)
+    const uint4* skip_table;
+    uint32_t skip_dim[3], skip_shift;
     const DNode* nodes;   // svo_rope (and the file-order view of the tree)
     const CNode* cnodes;  // svo_naive, svo_df, esvo
     // svo_naive: what find() reaches after its first top_levels levels, for each of the

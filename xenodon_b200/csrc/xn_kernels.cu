@@ -698,6 +698,295 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_TEX_MIN_BLOCKS) dda_tex_kern
 }
 
 // ---------------------------------------------------------------------------------
+// DDA over the texture residency with the skip table (resources/dda.comp:13-73, same arithmetic).
+//
+// Every ray still takes every step of the reference's march -- min of the side distances, the
+// axes that tie step together, t advances by the same binary32 additions -- so the sequence of
+// voxels, the segment lengths and the per-ray step counts are those of dda.comp.  What changes is
+// the fetch at dda.comp:45: on volumes that are mostly one colour (TNG gas: 90-96 % of voxels) the
+// skip table (xn_util_kernels.cu) tells a ray "travelling your way from this brick, every texel
+// within R_i voxels on axis i is colour uc", and texels the ray can know are not read.
+//
+// The promise is kept as a time, not a count.  Axis i takes its k-th step from now in the
+// iteration that ends at the side distance after k - 1 more additions of td_i, so the voxel a
+// step lands in is inside the promised box iff the step ends before
+//     t_safe = min_i(sd_i + R_i td_i) (1 - 2^-14)
+// (the factor bounds the rounding of up to ~1000 repeated additions from below).  A step advances
+// t by at most td_min, so a trip of four steps that starts before t_safe - 4.5 td_min lands on
+// promised texels only: one comparison per trip decides whether its four TEX are issued.  The
+// table is consulted again two trips before the promise runs out (usually the ray has entered
+// bricks that promise more by then), or at the exit of a mixed brick; a late or early look-up
+// only costs fetches, never correctness.
+//
+// Texels are consumed one trip after they were requested, as in dda_tex_kernel.  In the fast mode
+// the length of a known step goes to klen (through a 0/1 factor, on the FMA pipe: the ALU pipe --
+// min, compares -- is what bounds this kernel) and uc * klen is added when uc changes or the ray
+// ends; the strict mode accumulates uc * dt per step in the shader's order.  While every active
+// lane of the warp is in a known trip, the warp runs bare trips: geometry only.
+// ---------------------------------------------------------------------------------
+#ifndef XN_SKIP_MIN_BLOCKS
+#define XN_SKIP_MIN_BLOCKS 4
+#endif
+#ifndef XN_SKIP_BARE
+#define XN_SKIP_BARE 1
+#endif
+// look the table up this many trips before the promise runs out
+#ifndef XN_SKIP_EARLY
+#define XN_SKIP_EARLY 2
+#endif
+// experiment counters written to the STATS pass's byte counts instead of the algorithmic bytes:
+// 1 = steps taken in bare trips, 2 = table look-ups, 3 = texels fetched, 4 = known steps in full trips
+#ifndef XN_SKIP_DEBUG
+#define XN_SKIP_DEBUG 0
+#endif
+// a table colour (rgb bytes) as the texel type of the mode
+template <bool STRICT>
+struct TexUniform;
+template <>
+struct TexUniform<false> {
+    static __device__ __forceinline__ float4 texel_of(uint32_t rgb) {
+        const float r = 1.0f / 255.0f;
+        return make_float4((float)(rgb & 0xFFu) * r, (float)((rgb >> 8) & 0xFFu) * r, (float)((rgb >> 16) & 0xFFu) * r, 0.f);
+    }
+};
+template <>
+struct TexUniform<true> {
+    static __device__ __forceinline__ uchar4 texel_of(uint32_t rgb) {
+        return make_uchar4((unsigned char)(rgb & 0xFFu), (unsigned char)((rgb >> 8) & 0xFFu),
+                           (unsigned char)((rgb >> 16) & 0xFFu), 0);
+    }
+};
+
+template <bool STATS, bool STRICT>
+__global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
+    dda_skip_tex_kernel(const __grid_constant__ FrameParams p) {
+    typedef TexFetch<STRICT> TF;
+    typedef typename TF::texel texel;
+    uint32_t ix, iy;
+    thread_pixel<true>(p, ix, iy);
+    if (ix >= p.out_w || iy >= p.out_h) return;
+    RayStats<STATS> st;
+
+    const f3 rd = make_ray(p, p.out_x + (int32_t)ix, p.out_y + (int32_t)iy);
+    const float side = fmaxf((float)p.nx, fmaxf((float)p.ny, (float)p.nz));
+    f3 ro = F3(p.pos[0] * side, p.pos[1] * side, p.pos[2] * side);
+    const float ec = voxel_emission_coeff(p, rd) / side;
+
+    const f3 rrd = F3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+    const f3 bias = F3(rrd.x * ro.x, rrd.y * ro.y, rrd.z * ro.z);
+    const f3 bmin = F3(-bias.x, -bias.y, -bias.z);
+    const f3 bmax = F3((float)p.model_dim[0] * rrd.x - bias.x, (float)p.model_dim[1] * rrd.y - bias.y,
+                       (float)p.model_dim[2] * rrd.z - bias.z);
+    float t_min = max_elem(F3(gmin(bmin.x, bmax.x), gmin(bmin.y, bmax.y), gmin(bmin.z, bmax.z)));
+    const float t_max = min_elem(F3(gmax(bmin.x, bmax.x), gmax(bmin.y, bmax.y), gmax(bmin.z, bmax.z)));
+
+    TexAccum<STRICT> acc;
+    uint32_t uc = 0;   // colour of the current promise
+    float klen = 0.0f; // fast mode: length of known steps not yet added as uc * klen
+    if (!(t_min > t_max)) {
+        t_min = gmax(t_min, 0.0f);
+        ro = F3(ro.x + rd.x * t_min, ro.y + rd.y * t_min, ro.z + rd.z * t_min);
+        const float tdx = fabsf(rrd.x), tdy = fabsf(rrd.y), tdz = fabsf(rrd.z);
+        const f3 sg = F3(gsign(rd.x), gsign(rd.y), gsign(rd.z));
+        float sdx = (sg.x * ((floorf(ro.x) - ro.x) + 0.5f) + 0.5f) * tdx;
+        float sdy = (sg.y * ((floorf(ro.y) - ro.y) + 0.5f) + 0.5f) * tdy;
+        float sdz = (sg.z * ((floorf(ro.z) - ro.z) + 0.5f) + 0.5f) * tdz;
+        // ivec3(ro) truncates; texel centres are exact in binary32 (coordinates below 2^22)
+        float fx = (float)(int)ro.x + 0.5f, fy = (float)(int)ro.y + 0.5f, fz = (float)(int)ro.z + 0.5f;
+
+        const uint32_t S = p.skip_shift, BM = (1u << S) - 1u;
+        // voxels left to the brick face in the direction of travel: c ^ BM going up, c going down
+        const uint32_t xm = sg.x > 0.0f ? BM : 0u, ym = sg.y > 0.0f ? BM : 0u, zm = sg.z > 0.0f ? BM : 0u;
+        // octant of travel -> which radius byte of a table entry applies to this ray
+        const uint32_t oct = (sg.x > 0.0f ? 1u : 0u) | (sg.y > 0.0f ? 2u : 0u) | (sg.z > 0.0f ? 4u : 0u);
+        const uint32_t osh = 8u * (oct & 3u);
+        const float td_min = fminf(tdx, fminf(tdy, tdz));
+        const float td45 = 4.5f * td_min;
+        const float td_look = 8.0f * td_min;                    // spacing floor of table look-ups (two trips)
+        const float inv_trip = 1.0f / (4.00390625f * td_min);  // trips per unit of t, rounded down a little
+        float t_safe = -1.0f; // a step that ends before t_safe lands on a texel of colour uc
+        float t_look = 0.0f;  // consult the table at the first trip boundary at or after this time
+        texel uct = TF::zero(); // uc as a texel (strict mode)
+
+        texel v = TF::fetch(p, fx, fy, fz);
+        // 1.0 while the texel pending its segment was fetched, 0.0 while it is a known one (colour uc)
+        float pf = 1.0f;
+        float t = 0.0f;
+        const float t_end = t_max - t_min;
+        const float t_lim4 = t_end - td45;
+
+        // geometry of one step of dda.comp:41-50; DTV = its length
+#define XN_SKIP_GEOM(DTV)                                          \
+    {                                                              \
+        const float t0 = fminf(sdx, fminf(sdy, sdz));              \
+        const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0; \
+        DTV = t0 - t;                                              \
+        t = t0;                                                    \
+        if (mx) { sdx += tdx; fx += sg.x; }                        \
+        if (my) { sdy += tdy; fy += sg.y; }                        \
+        if (mz) { sdz += tdz; fz += sg.z; }                        \
+    }
+        // One step inside a trip.  The step's length belongs to the texel requested by the PREVIOUS
+        // step: FP = 1.0 if that one was fetched (DT = length) or 0.0 if it is known (length -> klen).
+        // FETCH (constant over the trip): request the texel of the voxel stepped into.
+#define XN_SKIP_STEP(DT, FP, TEXEL, FETCH)                         \
+    {                                                              \
+        float dt_;                                                 \
+        XN_SKIP_GEOM(dt_)                                          \
+        st.step();                                                 \
+        if (!XN_SKIP_DEBUG) st.read(4);                            \
+        if (STRICT) {                                              \
+            DT = dt_;                                              \
+        } else {                                                   \
+            DT = dt_ * FP;                                         \
+            klen = __fmaf_rn(dt_, 1.0f - FP, klen);                \
+        }                                                          \
+        if (XN_SKIP_DEBUG == 3 && FETCH) st.read(1);               \
+        if (XN_SKIP_DEBUG == 4 && !FETCH) st.read(1);              \
+        if (FETCH) TEXEL = TF::fetch(p, fx, fy, fz);               \
+        else if (STRICT) TEXEL = uct;                              \
+    }
+        // Table look-up at the current voxel (every active lane of the warp does it when any lane's
+        // promise is about to run out: a fresh promise never hurts, and the lanes' next look-ups
+        // move away together).  PEND = the texel pending its segment: if the promise changes colour
+        // while that texel is a known one, it is made explicit first.
+#define XN_SKIP_LOOKUP(PEND)                                                                                       \
+    {                                                                                                              \
+        if (XN_SKIP_DEBUG == 2) st.read(1);                                                                        \
+        const int vx = __float2int_rd(fx), vy = __float2int_rd(fy), vz = __float2int_rd(fz);                        \
+        /* beyond the table's border layer everything is border colour: clamp onto the layer */                    \
+        const uint32_t bx = (uint32_t)min(max((vx >> S) + 1, 0), (int)p.skip_dim[0] - 1);                           \
+        const uint32_t by = (uint32_t)min(max((vy >> S) + 1, 0), (int)p.skip_dim[1] - 1);                           \
+        const uint32_t bz = (uint32_t)min(max((vz >> S) + 1, 0), (int)p.skip_dim[2] - 1);                           \
+        const uint4 e = __ldg(p.skip_table + ((bz * p.skip_dim[1] + by) * p.skip_dim[0] + bx));                     \
+        const uint32_t k = ((oct & 4u ? e.w : e.z) >> osh) & 0xFFu; /* bricks of this colour ahead, 0 = mixed */    \
+        const uint32_t ext = k > 1u ? (k - 1u) << S : 0u;                                                          \
+        const float rx = (float)((((uint32_t)vx ^ xm) & BM) + ext), ry = (float)((((uint32_t)vy ^ ym) & BM) + ext), \
+                    rz = (float)((((uint32_t)vz ^ zm) & BM) + ext);                                                 \
+        const float te = fminf(sdx + rx * tdx, fminf(sdy + ry * tdy, sdz + rz * tdz)) * 0.99993896484375f;          \
+        float tl = te; /* mixed brick, or a short promise: look again when the ray is past it */                   \
+        if (k != 0u) {                                                                                             \
+            const uint32_t col = e.x & 0x00FFFFFFu;                                                                \
+            if (col != uc) {                                                                                       \
+                if (!STRICT) {                                                                                     \
+                    acc.add(TexUniform<STRICT>::texel_of(uc), klen);                                               \
+                    klen = 0.0f;                                                                                   \
+                    if (pf == 0.0f) {                                                                              \
+                        PEND = TexUniform<STRICT>::texel_of(uc);                                                   \
+                        pf = 1.0f;                                                                                 \
+                    }                                                                                              \
+                }                                                                                                  \
+                uc = col;                                                                                          \
+                if (STRICT) uct = TexUniform<STRICT>::texel_of(col);                                               \
+                t_safe = te;                                                                                       \
+            } else {                                                                                               \
+                t_safe = fmaxf(t_safe, te); /* both promises hold */                                               \
+            }                                                                                                      \
+            /* a promise worth at least three trips: renew it XN_SKIP_EARLY trips before it runs out */           \
+            if (t_safe - t > 3.0f * td45) tl = t_safe - (float)XN_SKIP_EARLY * td45;                              \
+        }                                                                                                          \
+        t_look = fmaxf(tl, t + td_look); /* and never within the next two trips */                                 \
+    }
+        // Between full trips: look-up when due, then as many bare trips -- four steps of geometry
+        // and nothing else -- as EVERY active lane of the warp is certain to spend on promised
+        // texels.  A step advances t by at most td_min, so lane i has at least
+        // floor((min(t_safe, t_end) - 4.5 td_min - t) / (4 td_min)) such trips ahead (none while a
+        // fetched texel is pending); the warp takes the minimum (one REDUX) and runs a counted loop.
+#define XN_SKIP_BARE_TRIPS(PEND)                                                                    \
+    {                                                                                               \
+        const unsigned am = __activemask();                                                         \
+        if (__any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                                      \
+        if (!STRICT && XN_SKIP_BARE) {                                                              \
+            const float x = ((fminf(t_safe, t_end) - td45) - t) * inv_trip;                         \
+            uint32_t ni = (pf == 0.0f && x > 0.0f) ? (uint32_t)fminf(x * 0.999999f, 1023.0f) + 1u : 0u; \
+            const uint32_t n = __reduce_min_sync(am, ni);                                           \
+            if (n != 0u) {                                                                          \
+                const float tb = t;                                                                 \
+                for (uint32_t k = 0; k < n; ++k) {                                                  \
+                    _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                 \
+                        float dt_;                                                                  \
+                        XN_SKIP_GEOM(dt_)                                                           \
+                        (void)dt_;                                                                  \
+                    }                                                                               \
+                }                                                                                   \
+                klen += t - tb;                                                                     \
+                if (STATS) {                                                                        \
+                    st.steps += 4u * n;                                                             \
+                    st.read(XN_SKIP_DEBUG == 0 ? 16u * n : (XN_SKIP_DEBUG == 1 ? 4u * n : 0u));     \
+                }                                                                                   \
+            }                                                                                       \
+        }                                                                                           \
+    }
+#define XN_SKIP_TRIP(N, P)                                  \
+    {                                                       \
+        const bool fetch = !(t < t_safe - td45);            \
+        const float nf = fetch ? 1.0f : 0.0f;               \
+        float d0;                                           \
+        XN_SKIP_STEP(d0, pf, N##0, fetch)                   \
+        XN_SKIP_STEP(N##d1, nf, N##1, fetch)                \
+        XN_SKIP_STEP(N##d2, nf, N##2, fetch)                \
+        XN_SKIP_STEP(N##d3, nf, N##3, fetch)                \
+        pf = nf;                                            \
+        acc.add(P##0, P##d1);                               \
+        acc.add(P##1, P##d2);                               \
+        acc.add(P##2, P##d3);                               \
+        acc.add(P##3, d0);                                  \
+    }
+#define XN_SKIP_FLUSH(P)       \
+    {                          \
+        acc.add(P##0, P##d1);  \
+        acc.add(P##1, P##d2);  \
+        acc.add(P##2, P##d3);  \
+        v = P##3;              \
+    }
+        if (t < t_lim4) {
+            texel a0 = TF::zero(), a1 = TF::zero(), a2 = TF::zero(), a3 = v;
+            texel b0 = TF::zero(), b1 = TF::zero(), b2 = TF::zero(), b3 = TF::zero();
+            float ad1 = 0.f, ad2 = 0.f, ad3 = 0.f, bd1 = 0.f, bd2 = 0.f, bd3 = 0.f;
+            for (;;) {
+                XN_SKIP_BARE_TRIPS(a3)
+                if (!(t < t_lim4)) { XN_SKIP_FLUSH(a) break; }
+                XN_SKIP_TRIP(b, a)
+                if (!(t < t_lim4)) { XN_SKIP_FLUSH(b) break; }
+                XN_SKIP_BARE_TRIPS(b3)
+                if (!(t < t_lim4)) { XN_SKIP_FLUSH(b) break; }
+                XN_SKIP_TRIP(a, b)
+                if (!(t < t_lim4)) { XN_SKIP_FLUSH(a) break; }
+            }
+        }
+        // the last few steps, one at a time (the promise in force still applies)
+        while (t < t_end) {
+            float dt;
+            texel vn = v;
+            float dt_;
+            XN_SKIP_GEOM(dt_)
+            st.step();
+            if (!XN_SKIP_DEBUG) st.read(4);
+            const bool fetch = !(t < t_safe);
+            if (STRICT) {
+                dt = dt_;
+            } else {
+                dt = dt_ * pf;
+                klen = __fmaf_rn(dt_, 1.0f - pf, klen);
+            }
+            if (fetch) vn = TF::fetch(p, fx, fy, fz);
+            else if (STRICT) vn = uct;
+            acc.add(v, dt);
+            v = vn;
+            pf = fetch ? 1.0f : 0.0f;
+        }
+#undef XN_SKIP_FLUSH
+#undef XN_SKIP_TRIP
+#undef XN_SKIP_BARE_TRIPS
+#undef XN_SKIP_LOOKUP
+#undef XN_SKIP_STEP
+#undef XN_SKIP_GEOM
+        if (!STRICT) acc.add(TexUniform<STRICT>::texel_of(uc), klen);
+    }
+    store_result(p, ix, iy, acc.finish(ec), st);
+}
+
+// ---------------------------------------------------------------------------------
 // shared octree helpers
 // ---------------------------------------------------------------------------------
 // Traversal stacks: [level][thread] in shared memory, addressed in the shared window directly
@@ -1368,7 +1657,8 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
         case 0:
             // XN_FORCE_IDX64=1 (test knob) runs the 64-bit-index kernel on small grids too
             if (p.tex_unorm != 0ull) { // texture residency
-                dda_tex_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p);
+                if (p.skip_table) dda_skip_tex_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p);
+                else dda_tex_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p);
             } else if (p.bk_slots != 0) { // bricked residency (xn_brick.h)
                 if (p.bk_slots <= (1ull << 32) && !force_idx64())
                     dda_kernel<STATS, STRICT, BrickCursor<false>><<<grid, block, 0, stream>>>(p);
@@ -1401,7 +1691,5 @@ cudaError_t launch_traversal(int traversal, const FrameParams& p, bool stats, bo
     if (stats) return strict ? launch_t<true, true>(traversal, p, stream) : launch_t<true, false>(traversal, p, stream);
     return strict ? launch_t<false, true>(traversal, p, stream) : launch_t<false, false>(traversal, p, stream);
 }
-
-cudaError_t configure_kernels() { return cudaSuccess; }
 
 } // namespace xn

@@ -6,7 +6,6 @@
 #include "xn_synth.h"
 
 namespace xn {
-cudaError_t configure_kernels();
 cudaError_t launch_traversal(int traversal, const FrameParams& p, bool stats, bool strict, cudaStream_t stream);
 cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth, cudaStream_t stream);
 // compact residency of the octree (internal nodes only, level order); *out is cudaMalloc'ed
@@ -28,6 +27,10 @@ cudaError_t launch_tiff_decode(const uint8_t* raw, uint32_t* slice, uint32_t W, 
 cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t stream);
 cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride, unsigned long long* out,
                                cudaStream_t stream);
+// DDA skip table over 2^shift-voxel bricks with radii up to `cap` (layout: xn_device.cuh SkipTable);
+// *table_out is cudaMalloc'ed, dims_out = table extent in bricks including the one-brick border
+cudaError_t build_skip_table(const uint32_t* grid, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift, uint32_t cap,
+                             uint4** table_out, uint32_t dims_out[3], cudaStream_t stream);
 cudaError_t launch_stats_totals(const uint32_t* steps, const unsigned long long* bytes, uint64_t n,
                                 unsigned long long* totals, cudaStream_t stream);
 } // namespace xn

@@ -290,6 +290,129 @@ cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------
+// DDA skip table (xn_device.cuh, FrameParams::skip_table): which B^3 bricks of the grid hold one
+// colour, and how far that colour extends in each of the eight directions of travel.  The DDA's
+// fetch (resources/dda.comp:45) is the only thing the table replaces: a ray still takes every
+// step of the reference's march, but texels the table lets it know are not read.
+//   entry (16 bytes) = { x: rgb | uniform << 24, y: 0, z: radius bytes of octants 0-3, w: 4-7 }
+//   octant o = (dir.x > 0) | (dir.y > 0) << 1 | (dir.z > 0) << 2.
+//   radius k of octant o (0 for a mixed brick): the k^3 bricks b + s * [0, k)^3, s = the octant's
+//   signs, all hold this one colour -- so a ray travelling in octant o from any voxel of the brick
+//   finds this colour for R_i = r_i + (k - 1) B voxels on axis i, r_i = voxels left to the brick
+//   face.  (Largest-cube dynamic programme: k(b) = 1 + min over the seven bricks b + s * delta.)
+// The table has a one-brick border on every side standing for the sampler's border colour
+// (transparent black, src/render/DdaRaytraceAlgorithm.cpp:26-29); voxels of an edge brick that
+// lie outside the grid count as black too.  Alpha is ignored: the march reads texel.rgb only.
+// ---------------------------------------------------------------------------------
+constexpr uint32_t SKIP_UNIFORM = 1u << 24;
+
+__global__ void skip_classify_kernel(const uint32_t* __restrict__ grid, uint32_t nx, uint32_t ny, uint32_t nz,
+                                     uint32_t shift, uint32_t tx, uint32_t ty, uint4* __restrict__ table) {
+    // one block per brick; thread = one x row of the brick
+    const uint32_t B = 1u << shift;
+    const uint32_t bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    const uint32_t x0 = bx << shift, y0 = by << shift, z0 = bz << shift;
+    const uint32_t ref = grid[(uint64_t)x0 + (uint64_t)y0 * nx + (uint64_t)z0 * nx * ny] & 0x00FFFFFFu;
+    bool same = true;
+    for (uint32_t row = threadIdx.x; row < B * B; row += blockDim.x) {
+        const uint32_t y = y0 + (row & (B - 1u)), z = z0 + (row >> shift);
+        if (y < ny && z < nz) {
+            const uint32_t* r = grid + ((uint64_t)y * nx + (uint64_t)z * nx * ny);
+            for (uint32_t x = x0; x < x0 + B; ++x) same &= ((x < nx ? r[x] : 0u) & 0x00FFFFFFu) == ref;
+        } else {
+            same &= ref == 0u;
+        }
+    }
+    same = __syncthreads_and(same) != 0;
+    if (threadIdx.x == 0)
+        table[((uint64_t)(bz + 1u) * ty + (by + 1u)) * tx + (bx + 1u)] =
+            same ? make_uint4(ref | SKIP_UNIFORM, 0u, 0x01010101u, 0x01010101u) : make_uint4(ref, 0u, 0u, 0u);
+}
+
+__global__ void skip_fill_kernel(uint4* __restrict__ table, uint64_t n, uint4 value) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        table[i] = value;
+}
+
+// one relaxation step of the eight radii: k' = 1 + min over the seven bricks one step along the
+// octant of (same colour ? their k : 0), capped; beyond the table everything is border colour
+// with unbounded radius.  Starting from k = 1, iteration n yields min(true k, n + 1).
+__global__ void skip_relax_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t tx, uint32_t ty,
+                                  uint32_t tz, uint32_t cap) {
+    const uint64_t n = (uint64_t)tx * ty * tz;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 e = in[i];
+        if (e.x & SKIP_UNIFORM) {
+            const int x = (int)(i % tx), y = (int)((i / tx) % ty), z = (int)(i / ((uint64_t)tx * ty));
+            const uint32_t beyond = (e.x & 0x00FFFFFFu) == 0u ? cap : 0u;
+            // radii of the 26 neighbours in their own octant directions are read per octant below;
+            // a neighbour of another colour (or a mixed one) contributes 0
+            uint32_t lo = 0, hi = 0;
+            for (uint32_t o = 0; o < 8u; ++o) {
+                const int sx = (o & 1u) ? 1 : -1, sy = (o & 2u) ? 1 : -1, sz = (o & 4u) ? 1 : -1;
+                uint32_t m = cap;
+                for (uint32_t dl = 1; dl < 8u; ++dl) {
+                    const int X = x + ((dl & 1u) ? sx : 0), Y = y + ((dl & 2u) ? sy : 0), Z = z + ((dl & 4u) ? sz : 0);
+                    uint32_t nd;
+                    if (X < 0 || Y < 0 || Z < 0 || X >= (int)tx || Y >= (int)ty || Z >= (int)tz) {
+                        nd = beyond;
+                    } else {
+                        const uint4 ne = in[((uint64_t)Z * ty + Y) * tx + X];
+                        nd = ne.x == e.x ? (((o < 4u ? ne.z : ne.w) >> (8u * (o & 3u))) & 0xFFu) : 0u;
+                    }
+                    m = min(m, nd);
+                }
+                const uint32_t k = min(cap, m + 1u);
+                if (o < 4u) lo |= k << (8u * o);
+                else hi |= k << (8u * (o - 4u));
+            }
+            e.z = lo;
+            e.w = hi;
+        }
+        out[i] = e;
+    }
+}
+
+cudaError_t build_skip_table(const uint32_t* grid, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift, uint32_t cap,
+                             uint4** table_out, uint32_t dims_out[3], cudaStream_t stream) {
+    *table_out = nullptr;
+    if (shift < 1u || shift > 5u || cap < 1u || cap > 255u) return cudaErrorInvalidValue;
+    // the march's promise covers at most (cap - 1) B + B - 1 steps per axis; the rounding bound of
+    // the kernel's t_safe (a factor 1 - 2^-14) holds for up to ~1000 repeated additions
+    while (cap > 1u && ((cap << shift) > 1000u)) --cap;
+    const uint32_t B = 1u << shift;
+    const uint32_t bx = (nx + B - 1u) >> shift, by = (ny + B - 1u) >> shift, bz = (nz + B - 1u) >> shift;
+    if (by > 65535u || bz > 65535u) return cudaErrorInvalidValue;
+    const uint32_t tx = bx + 2u, ty = by + 2u, tz = bz + 2u;
+    const uint64_t n = (uint64_t)tx * ty * tz;
+    if (n >= (1ull << 31)) return cudaErrorInvalidValue; // the kernel indexes the table with 32 bits
+    uint4 *a = nullptr, *b = nullptr;
+    cudaError_t e = cudaMalloc(&a, n * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&b, n * sizeof(uint4));
+    if (e == cudaSuccess) {
+        // border: black, radius 1 so far
+        skip_fill_kernel<<<148 * 8, 256, 0, stream>>>(a, n, make_uint4(SKIP_UNIFORM, 0u, 0x01010101u, 0x01010101u));
+        skip_classify_kernel<<<dim3(bx, by, bz), B * B < 64u ? B * B : 64u, 0, stream>>>(grid, nx, ny, nz, shift, tx, ty, a);
+        for (uint32_t it = 1; it < cap; ++it) {
+            skip_relax_kernel<<<148 * 8, 256, 0, stream>>>(a, b, tx, ty, tz, cap);
+            uint4* t = a;
+            a = b;
+            b = t;
+        }
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
+    cudaFree(b);
+    if (e != cudaSuccess) {
+        cudaFree(a);
+        return e;
+    }
+    *table_out = a;
+    dims_out[0] = tx, dims_out[1] = ty, dims_out[2] = tz;
+    return cudaSuccess;
+}
+
 // sum reduction of the stats arrays (totals for the roofline accounting)
 __global__ void stats_totals_kernel(const uint32_t* __restrict__ steps, const unsigned long long* __restrict__ bytes,
                                     uint64_t n, unsigned long long* __restrict__ totals) {

@@ -804,6 +804,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         const float td45 = 4.5f * td_min;
         const float td_look = 8.0f * td_min;                    // spacing floor of table look-ups (two trips)
         const float inv_trip = 1.0f / (4.00390625f * td_min);  // trips per unit of t, rounded down a little
+        const float itdx = 1.0f / tdx, itdy = 1.0f / tdy, itdz = 1.0f / tdz;
+        // longest bare run, in trips minus one: an axis' side distance takes at most 4 n + 1 additions in
+        // n trips, each rounded by at most 2^-24 (t_end + td_i), so the step count recovered from it is
+        // off by less than (4 n + 1) 2^-24 (t_end / td_min + 1) -- kept below a quarter
+        const float n_cap = fminf(1022.0f, fmaxf(65536.0f * td_min / ((t_max - fmaxf(t_min, 0.0f)) + td_min) * 15.9f - 2.0f, 0.0f));
         float t_safe = -1.0f; // a step that ends before t_safe lands on a texel of colour uc
         float t_look = 0.0f;  // consult the table at the first trip boundary at or after this time
         texel uct = TF::zero(); // uc as a texel (strict mode)
@@ -898,17 +903,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         if (__any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                                      \
         if (!STRICT && XN_SKIP_BARE) {                                                              \
             const float x = ((fminf(t_safe, t_end) - td45) - t) * inv_trip;                         \
-            uint32_t ni = (pf == 0.0f && x > 0.0f) ? (uint32_t)fminf(x * 0.999999f, 1023.0f) + 1u : 0u; \
+            uint32_t ni = (pf == 0.0f && x > 0.0f) ? (uint32_t)fminf(x * 0.999999f, n_cap) + 1u : 0u; \
             const uint32_t n = __reduce_min_sync(am, ni);                                           \
             if (n != 0u) {                                                                          \
-                const float tb = t;                                                                 \
+                /* positions are not needed while nothing is fetched: the run advances the side */  \
+                /* distances only, and the texel centres follow from how often each axis stepped, */ \
+                /* k_i = round((sd_i - sd_i before) / td_i) -- exact, the run is capped (n_cap) so  */ \
+                /* that the rounding of its additions stays below a quarter of a step             */ \
+                const float tb = t, sx0 = sdx, sy0 = sdy, sz0 = sdz;                                \
                 for (uint32_t k = 0; k < n; ++k) {                                                  \
                     _Pragma("unroll") for (int q = 0; q < 4; ++q) {                                 \
-                        float dt_;                                                                  \
-                        XN_SKIP_GEOM(dt_)                                                           \
-                        (void)dt_;                                                                  \
+                        const float t0 = fminf(sdx, fminf(sdy, sdz));                               \
+                        const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0;                  \
+                        t = t0;                                                                     \
+                        if (mx) sdx += tdx;                                                         \
+                        if (my) sdy += tdy;                                                         \
+                        if (mz) sdz += tdz;                                                         \
                     }                                                                               \
                 }                                                                                   \
+                fx = __fmaf_rn(sg.x, rintf((sdx - sx0) * itdx), fx);                                \
+                fy = __fmaf_rn(sg.y, rintf((sdy - sy0) * itdy), fy);                                \
+                fz = __fmaf_rn(sg.z, rintf((sdz - sz0) * itdz), fz);                                \
                 klen += t - tb;                                                                     \
                 if (STATS) {                                                                        \
                     st.steps += 4u * n;                                                             \

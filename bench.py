@@ -348,6 +348,14 @@ class SharedHostFrames:
         self.flag_bytes = 4096
         size = self.flag_bytes + count * self.frame_bytes
         self.shm = shared_memory.SharedMemory(name=name, create=create, size=size)
+        if not create:
+            # only the creating rank owns the segment: keep this process's resource tracker from
+            # unlinking (and warning about) a segment it merely attached to
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
         self.base = self.buf.ctypes.data
         xb.host_register(self.base, size)
@@ -724,12 +732,6 @@ def main():
     if single:
         result["single_gpu_same_workload"] = single
 
-    if extras:
-        try:
-            result["per_config"] = per_config_block(xb, ctx, workload, traversal, result, steps, warmup, local_rank)
-        except Exception as e:  # extras must never take the headline down with them
-            result["per_config"] = {"error": str(e)}
-
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
     if extras:
         try:
@@ -759,6 +761,12 @@ def main():
                                       "max_diff": int(d.max())}
         except Exception as e:  # the baseline must never take the GPU number down with it
             result["cpu_baseline"] = {"error": str(e)}
+
+    if extras:
+        try:
+            result["per_config"] = per_config_block(xb, ctx, workload, traversal, result, steps, warmup, local_rank)
+        except Exception as e:  # extras must never take the headline down with them
+            result["per_config"] = {"error": str(e)}
 
     print(json.dumps(result), file=_JSON_OUT, flush=True)
     if shared:

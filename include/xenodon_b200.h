@@ -210,6 +210,20 @@ XN_API int xn_render_download_async(xn_ctx* ctx, int traversal, const float forw
                                     const float translation[3], uint32_t* host_dst);
 XN_API int xn_host_alloc(size_t bytes, void** out); /* page-locked host memory */
 XN_API int xn_host_free(void* p);
+/* The same pipeline for a frame that several devices (or processes, one per GPU) assemble directly
+ * in host memory -- HeadlessDisplay::save's composite (src/backend/headless/HeadlessDisplay.cpp:59-76)
+ * without a gathering device: host_frame is the ENCLOSING frame's pixel (region.x, region.y),
+ * stride_px its row stride; only the rows this context owns (all rows, or its 16-row stripes under
+ * xn_set_interleave) are written, so N contexts sharing one page-locked frame fill it over N
+ * PCIe links.  xn_host_register page-locks memory the caller mapped itself (e.g. POSIX shared
+ * memory mapped by every process).  xn_signal_after_copy stores `value` to *host_flag (release
+ * order) once every copy enqueued so far on this context has landed: the consumer polls the flags
+ * instead of synchronising with the producers. */
+XN_API int xn_render_download_to(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                                 const float translation[3], uint32_t* host_frame, size_t stride_px);
+XN_API int xn_signal_after_copy(xn_ctx* ctx, volatile uint32_t* host_flag, uint32_t value);
+XN_API int xn_host_register(void* p, size_t bytes);
+XN_API int xn_host_unregister(void* p);
 
 /* Device-side stopwatch over any span of calls on this context: xn_mark(ctx, 0) and
  * xn_mark(ctx, 1) record events on the context's stream; xn_mark_elapsed waits for the

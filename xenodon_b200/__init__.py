@@ -103,6 +103,11 @@ _PROTOTYPES = {
     "xn_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "xn_render_download_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
                                            C.POINTER(C.c_float * 3), C.c_void_p]),
+    "xn_render_download_to": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
+                                        C.POINTER(C.c_float * 3), C.c_void_p, C.c_size_t]),
+    "xn_signal_after_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "xn_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "xn_host_unregister": (C.c_int, [C.c_void_p]),
     "xn_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "xn_host_free": (C.c_int, [C.c_void_p]),
     "xn_mark": (C.c_int, [C.c_void_p, C.c_int]),
@@ -424,6 +429,15 @@ class Context:
         f, u, p = _f3(camera[0]), _f3(camera[1]), _f3(camera[2])
         _check(lib().xn_render_download_async(self._h, t, C.byref(f), C.byref(u), C.byref(p), host_frame.ptr))
 
+    def render_download_to(self, traversal, camera, host_frame_ptr: int, stride_px: int):
+        """Pipelined frame whose owned rows (all, or this context's stripes) land in a shared host frame."""
+        t = TRAVERSALS[traversal] if isinstance(traversal, str) else traversal
+        f, u, p = _f3(camera[0]), _f3(camera[1]), _f3(camera[2])
+        _check(lib().xn_render_download_to(self._h, t, C.byref(f), C.byref(u), C.byref(p), host_frame_ptr, stride_px))
+
+    def signal_after_copy(self, host_flag_ptr: int, value: int):
+        _check(lib().xn_signal_after_copy(self._h, host_flag_ptr, value))
+
     def mark(self, which: int):
         _check(lib().xn_mark(self._h, which))
 
@@ -498,6 +512,15 @@ class PinnedFrame:
             self.array = None
             lib().xn_host_free(self.ptr)
             self.ptr = None
+
+
+def host_register(ptr: int, nbytes: int):
+    """Page-lock memory the caller mapped itself (shared memory seen by several processes)."""
+    _check(lib().xn_host_register(ptr, nbytes))
+
+
+def host_unregister(ptr: int):
+    _check(lib().xn_host_unregister(ptr))
 
 
 def _frame_buffer_read_async(self, ptr: int, w: int, h: int, pinned: "PinnedFrame"):

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "host/xn_host.hpp"
@@ -79,6 +80,7 @@ struct xn_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
+    cudaEvent_t ev_gather = nullptr; // "this context's frame is rendered", waited on by xn_frame_gather
     bool timing_pending = false;
     uint64_t launches = 0;
 
@@ -525,6 +527,7 @@ int xn_ctx_create(int cuda_device, xn_ctx** out) {
         XN_CUDA(cudaEventCreate(&ctx->ev_stop));
         XN_CUDA(cudaEventCreate(&ctx->ev_mark[0]));
         XN_CUDA(cudaEventCreate(&ctx->ev_mark[1]));
+        XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
         XN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
@@ -553,6 +556,7 @@ int xn_ctx_destroy(xn_ctx* ctx) {
         if (ctx->own_target) cudaFree(ctx->own_target);
         cudaEventDestroy(ctx->ev_start);
         cudaEventDestroy(ctx->ev_stop);
+        if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
         cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -966,46 +970,130 @@ int xn_render(xn_ctx* ctx, int traversal, const float forward[3], const float up
     });
 }
 
+namespace {
+// Pipelined frame: traversal into one of two alternating device targets, then the region's OWNED
+// rows (all of them, or this context's 16-row stripes under xn_set_interleave) copied to
+// host_dst[y * stride_px + x] on the copy stream.
+void render_download(xn_ctx* ctx, int traversal, const float forward[3], const float up[3], const float translation[3],
+                     uint32_t* host_dst, size_t stride_px) {
+    check_ctx(ctx);
+    if (!host_dst) throw xn::Error(XN_ERR_INVALID, "null destination");
+    if (ctx->ext_target) throw xn::Error(XN_ERR_INVALID, "pipelined output cannot target an external buffer");
+    xn::FrameParams p;
+    fill_params(ctx, traversal, forward, up, translation, p);
+    if (stride_px == 0) stride_px = p.out_w;
+    if (stride_px < p.out_w) throw xn::Error(XN_ERR_INVALID, "stride smaller than the region width");
+    DeviceGuard g(ctx->device);
+    const uint64_t px = (uint64_t)p.out_w * p.out_h;
+    if (px == 0) return;
+    if (px > ctx->pipe_target_px) {
+        XN_CUDA(cudaStreamSynchronize(ctx->stream));
+        XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
+            ctx->pipe_target[i] = nullptr;
+            ctx->copy_in_flight[i] = false;
+        }
+        ctx->pipe_target_px = 0;
+        XN_CUDA(cudaMalloc(&ctx->pipe_target[0], px * 4));
+        XN_CUDA(cudaMalloc(&ctx->pipe_target[1], px * 4));
+        ctx->pipe_target_px = px;
+    }
+    const int b = ctx->pipe_next;
+    ctx->pipe_next ^= 1;
+    // the traversal may only overwrite target b once its previous copy-out has finished
+    if (ctx->copy_in_flight[b]) XN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    p.target = ctx->pipe_target[b];
+    p.target_stride = p.out_w;
+    XN_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+    XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->strict, ctx->stream));
+    XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    XN_CUDA(cudaEventRecord(ctx->ev_rendered[b], ctx->stream));
+    XN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[b], 0));
+    const uint32_t* src = ctx->pipe_target[b];
+    if (ctx->il_count <= 1 && stride_px == p.out_w) {
+        XN_CUDA(cudaMemcpyAsync(host_dst, src, px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    } else if (ctx->il_count <= 1) {
+        XN_CUDA(cudaMemcpy2DAsync(host_dst, stride_px * 4, src, (size_t)p.out_w * 4, (size_t)p.out_w * 4, p.out_h,
+                                  cudaMemcpyDeviceToHost, ctx->copy_stream));
+    } else {
+        // owned stripes: BLOCK_H rows each, il_count stripes apart.  With tight rows a stripe is one
+        // contiguous run, so all full stripes go in ONE 2-D copy (row = a stripe); a ragged last
+        // stripe (frame height not a multiple of 16) follows on its own.
+        const uint32_t bh = xn::BLOCK_H;
+        const uint32_t stripes = (p.out_h + bh - 1) / bh;
+        const uint32_t first = ctx->il_index;
+        uint32_t full = 0, last_rows = 0, last_stripe = 0;
+        for (uint32_t s = first; s < stripes; s += ctx->il_count) {
+            const uint32_t rows = std::min<uint32_t>(bh, p.out_h - s * bh);
+            if (rows == bh) ++full;
+            else last_rows = rows, last_stripe = s;
+        }
+        if (stride_px == p.out_w) {
+            const size_t run = (size_t)bh * p.out_w * 4, pitch = run * ctx->il_count;
+            const size_t off = (size_t)first * bh * p.out_w;
+            if (full)
+                XN_CUDA(cudaMemcpy2DAsync(host_dst + off, pitch, src + off, pitch, run, full, cudaMemcpyDeviceToHost,
+                                          ctx->copy_stream));
+        } else {
+            for (uint32_t s = first, k = 0; k < full; s += ctx->il_count, ++k)
+                XN_CUDA(cudaMemcpy2DAsync(host_dst + (size_t)s * bh * stride_px, stride_px * 4,
+                                          src + (size_t)s * bh * p.out_w, (size_t)p.out_w * 4, (size_t)p.out_w * 4, bh,
+                                          cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        if (last_rows)
+            XN_CUDA(cudaMemcpy2DAsync(host_dst + (size_t)last_stripe * bh * stride_px, stride_px * 4,
+                                      src + (size_t)last_stripe * bh * p.out_w, (size_t)p.out_w * 4, (size_t)p.out_w * 4,
+                                      last_rows, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    XN_CUDA(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+    ctx->copy_in_flight[b] = true;
+    ctx->timing_pending = true;
+    ++ctx->launches;
+}
+
+void CUDART_CB write_flag_cb(void* arg) {
+    // arg packs nothing: the pair lives in a heap cell so that the callback can free it
+    auto* cell = static_cast<std::pair<volatile uint32_t*, uint32_t>*>(arg);
+    __atomic_store_n(const_cast<uint32_t*>(cell->first), cell->second, __ATOMIC_RELEASE);
+    delete cell;
+}
+} // namespace
+
 int xn_render_download_async(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
                              const float translation[3], uint32_t* host_dst) {
+    return guarded([&] { render_download(ctx, traversal, forward, up, translation, host_dst, 0); });
+}
+
+int xn_render_download_to(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
+                          const float translation[3], uint32_t* host_frame, size_t stride_px) {
+    return guarded([&] { render_download(ctx, traversal, forward, up, translation, host_frame, stride_px); });
+}
+
+int xn_signal_after_copy(xn_ctx* ctx, volatile uint32_t* host_flag, uint32_t value) {
     return guarded([&] {
         check_ctx(ctx);
-        if (!host_dst) throw xn::Error(XN_ERR_INVALID, "null destination");
-        if (ctx->ext_target) throw xn::Error(XN_ERR_INVALID, "pipelined output cannot target an external buffer");
-        xn::FrameParams p;
-        fill_params(ctx, traversal, forward, up, translation, p);
+        if (!host_flag) throw xn::Error(XN_ERR_INVALID, "null flag");
         DeviceGuard g(ctx->device);
-        const uint64_t px = (uint64_t)p.out_w * p.out_h;
-        if (px == 0) return;
-        if (px > ctx->pipe_target_px) {
-            XN_CUDA(cudaStreamSynchronize(ctx->stream));
-            XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-            for (int i = 0; i < 2; ++i) {
-                if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
-                ctx->pipe_target[i] = nullptr;
-                ctx->copy_in_flight[i] = false;
-            }
-            ctx->pipe_target_px = 0;
-            XN_CUDA(cudaMalloc(&ctx->pipe_target[0], px * 4));
-            XN_CUDA(cudaMalloc(&ctx->pipe_target[1], px * 4));
-            ctx->pipe_target_px = px;
+        auto* cell = new std::pair<volatile uint32_t*, uint32_t>(host_flag, value);
+        const cudaError_t e = cudaLaunchHostFunc(ctx->copy_stream, write_flag_cb, cell);
+        if (e != cudaSuccess) {
+            delete cell;
+            throw CudaError{e, "cudaLaunchHostFunc"};
         }
-        const int b = ctx->pipe_next;
-        ctx->pipe_next ^= 1;
-        // the traversal may only overwrite target b once its previous copy-out has finished
-        if (ctx->copy_in_flight[b]) XN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-        p.target = ctx->pipe_target[b];
-        p.target_stride = p.out_w;
-        XN_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
-        XN_CUDA(xn::launch_traversal(traversal, p, false, ctx->strict, ctx->stream));
-        XN_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
-        XN_CUDA(cudaEventRecord(ctx->ev_rendered[b], ctx->stream));
-        XN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[b], 0));
-        XN_CUDA(cudaMemcpyAsync(host_dst, ctx->pipe_target[b], px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        XN_CUDA(cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
-        ctx->copy_in_flight[b] = true;
-        ctx->timing_pending = true;
-        ++ctx->launches;
+    });
+}
+
+int xn_host_register(void* p, size_t bytes) {
+    return guarded([&] {
+        if (!p || bytes == 0) throw xn::Error(XN_ERR_INVALID, "bad arguments");
+        XN_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    });
+}
+
+int xn_host_unregister(void* p) {
+    return guarded([&] {
+        if (p) XN_CUDA(cudaHostUnregister(p));
     });
 }
 
@@ -1177,6 +1265,13 @@ int xn_frame_gather(xn_ctx* const* ctxs, int n, uint32_t* host_dst, xn_rect* enc
                 const uint32_t* src = c->ext_target ? c->ext_target : c->own_target;
                 const size_t src_stride = c->ext_target ? c->ext_stride : c->output.w;
                 uint32_t* dst = frame + (uint64_t)(c->output.y - enc.y) * enc.w + (uint64_t)(c->output.x - enc.x);
+                if (c != root) {
+                    // the tile is read on the root's stream: order the read after the work already
+                    // enqueued on the tile's own stream (the caller need not have synchronised it)
+                    DeviceGuard gc(c->device);
+                    XN_CUDA(cudaEventRecord(c->ev_gather, c->stream));
+                    XN_CUDA(cudaStreamWaitEvent(root->stream, c->ev_gather, 0));
+                }
                 // UVA peer copy: goes over NVLink when peer access is possible, staged otherwise
                 XN_CUDA(cudaMemcpy2DAsync(dst, (size_t)enc.w * 4, src, src_stride * 4, (size_t)c->output.w * 4,
                                           c->output.h, cudaMemcpyDefault, root->stream));

@@ -273,7 +273,7 @@ XN_API int xn_tiff_read(const char* path, uint8_t* rgba_out, uint64_t cap_bytes)
 /* How xn_upload_grid_tiff will take the file (host arithmetic only): streamable = 1 when every
  * layer is uncompressed chunky 8-bit strips of one sample layout (decoded on the device), 0 when
  * the host decoder is used (tiles, mixed layouts).  format_out (nullable) = samples per pixel,
- * photometric, has alpha, alpha is unassociated, rows are flipped; runs_out (nullable) = number
+ * photometric, has alpha, alpha is unassociated, orientation flips (bit 0 rows, bit 1 columns reversed); runs_out (nullable) = number
  * of contiguous file ranges read (adjacent strips are merged). */
 XN_API int xn_tiff_stream_info(const char* path, int* streamable_out, uint32_t format_out[5], uint64_t* runs_out);
 /* writer used to make inputs (uncompressed contiguous RGBA, one directory per z) */

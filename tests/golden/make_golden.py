@@ -39,7 +39,25 @@ def render_cases():
     ]
 
 
+def orientation_fixtures():
+    """Every value of the Orientation tag (274) through the real libtiff (Grid::load_tiff ->
+    TIFFReadRGBAImage): which of them reverse rows, columns, both or neither."""
+    from util import write_tiff
+    rng = np.random.default_rng(274)
+    layers = [rng.integers(0, 256, (4, 5, 3), dtype=np.uint8) for _ in range(2)]
+    out = {}
+    for o in range(1, 9):
+        name = f"orient_{o}.tif"
+        write_tiff(os.path.join(HERE, name), layers, photometric=2, orientation=o, rows_per_strip=3)
+        out[name] = xref_model.load_tiff(os.path.join(HERE, name))
+    np.savez_compressed(os.path.join(HERE, "tiff_orient_golden.npz"), **out)
+
+
 def main():
+    if "--only-orientation" in sys.argv:
+        assert xref_model.available(), "build oracle/_ref first (make -C oracle ref)"
+        orientation_fixtures()
+        return
     assert xref.available() and xref_model.available(), "build oracle/_ref first (make -C oracle ref)"
     out = {}
     tmp = os.path.join(HERE, "_tmp.svo")
@@ -110,6 +128,7 @@ def main():
         write_tiff_layout(os.path.join(HERE, name), spp, phot, extra)
         tiff[name] = xref_model.load_tiff(os.path.join(HERE, name))
     np.savez_compressed(os.path.join(HERE, "tiff_golden.npz"), **tiff)
+    orientation_fixtures()
     print("golden fixtures written to", HERE)
 
 

@@ -1,6 +1,7 @@
 """`xenodon convert` on the GPU (xn_convert_resident_grid): the node array must be byte-identical
-to the host builder's (itself pinned against the reference's own code), for sparse and rope
-trees, any threshold, grids that are not powers of two, and through to rendering."""
+to the oracle's restatement of the reference builder (oracle/xn_oracle.c, itself pinned against the
+reference's own src/model code) and to the product's host builder, for sparse and rope trees, any
+threshold, grids that are not powers of two, and through to rendering."""
 import numpy as np
 import pytest
 
@@ -20,7 +21,7 @@ def _gpu_convert(xb, g, **kw):
 
 @pytest.mark.parametrize("dims", [(1, 1, 1), (2, 2, 2), (3, 3, 3), (8, 8, 8), (16, 11, 16), (20, 9, 5), (40, 33, 17),
                                   (64, 64, 64), (33, 70, 12)])
-def test_gpu_convert_matches_host_builder(xb, dims):
+def test_gpu_convert_matches_host_builder(xb, xo, dims):
     rng = np.random.default_rng(sum(dims) * 7 + 1)
     grids = [random_grid(rng, *dims, quant=64), blobby_grid(rng, *dims), np.full((dims[2], dims[1], dims[0], 4), 77, np.uint8),
              rng.integers(0, 256, (dims[2], dims[1], dims[0], 4), dtype=np.uint8)]
@@ -28,10 +29,12 @@ def test_gpu_convert_matches_host_builder(xb, dims):
         for ttype in (xb.TYPE_SPARSE, xb.TYPE_ROPE):
             for thr in (0, 60, 255):
                 tree, st, count, side = _gpu_convert(xb, g, chan_diff=thr, type=ttype)
-                ref, rst = xb.build_octree(xb.Grid(g), chan_diff=thr, type=ttype)
-                assert (count, side) == (len(ref.nodes), ref.side)
-                assert tree.nodes.tobytes() == ref.nodes.tobytes(), (dims, ttype, thr)
-                assert st == rst, (dims, ttype, thr, st, rst)
+                onodes, oside, ost = xo.build_octree(g, chan_diff=thr, type=ttype)  # the oracle, directly
+                assert (count, side) == (len(onodes), oside)
+                assert tree.nodes.tobytes() == onodes.tobytes(), (dims, ttype, thr)
+                assert st == ost, (dims, ttype, thr, st, ost)
+                ref, rst = xb.build_octree(xb.Grid(g), chan_diff=thr, type=ttype)  # and the product's host builder
+                assert tree.nodes.tobytes() == ref.nodes.tobytes() and st == rst, (dims, ttype, thr)
 
 
 def test_gpu_convert_synthetic_volumes_and_render(xb, xo):

@@ -32,7 +32,7 @@ def _cam(f):
 
 
 def test_gpu_octree_of_the_full_volume_is_byte_identical_to_the_host_builder(xb, scene):
-    ref, rst = xb.build_octree(scene["host"], chan_diff=0, type=xb.TYPE_ROPE)
+    ref, rst = xb.build_octree(scene["host"], chan_diff=0, type=xb.TYPE_ROPE)  # product host builder (pinned to the reference digests on CPU)
     assert len(ref.nodes) == len(scene["tree"].nodes) > 10_000_000
     assert ref.nodes.tobytes() == scene["tree"].nodes.tobytes()
     assert rst == scene["stats"] and rst["depth"] == 9
@@ -177,5 +177,71 @@ def test_grid_residency_layouts_agree_at_large_sizes(xb, dims, big):
                     assert (d <= 1).mean() >= 0.999, (t, i, float((d <= 1).mean()), int(d.max()))
                 d = np.abs(imgs["esvo"] - out[(xb.LAYOUT_LINEAR, True, i)][0].astype(int)).max(axis=-1)
                 assert (d <= 1).mean() >= 0.95, (i, float((d <= 1).mean()))
+    finally:
+        ctx.close()
+
+
+# ---- direct oracle parity at BASELINE configs 3, 4 and 5 (1024^3, the full 2048^3, the 8K frame) ----
+def _rows_vs_oracle(xo, ctx, traversal, cam, frame, rows, *, grid=None, tree=None, emission=EMISSION, tag=""):
+    """Strict-mode image and per-ray step counts of `rows` = [(y0, n)] against the oracle; the
+    fast-mode image of the same rows must stay within 1/255 with identical step counts."""
+    w, h = frame
+    out = {}
+    for strict in (True, False):
+        ctx.set_precision(strict)
+        ctx.render(traversal, cam)
+        ctx.sync()
+        out[strict] = (ctx.download(), ctx.stats_pass(traversal, cam)[0])
+    assert out[True][0][..., :3].any(), tag
+    assert np.array_equal(out[True][1], out[False][1]), tag
+    for (y0, n) in rows:
+        kw = dict(camera=cam, output=(0, y0, w, n), display=(0, 0, w, h), emission=emission, threads=0)
+        if traversal == "dda":
+            ref, rsteps, _ = xo.render("dda", grid=grid, **kw)
+        else:
+            ref, rsteps, _ = xo.render(traversal, nodes=tree.nodes, side=tree.side, **kw)
+        assert np.array_equal(out[True][1][y0:y0 + n], rsteps), (tag, traversal, y0)
+        assert np.array_equal(out[True][0][y0:y0 + n], ref), (tag, traversal, y0)
+        d = np.abs(out[False][0][y0:y0 + n].astype(int) - ref.astype(int))
+        assert d.max() <= 1, (tag, traversal, y0, int(d.max()))
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_big_volumes_match_the_oracle_directly(xb, xo, n):
+    """BASELINE configs 3 and 4: the 1024^3 and the full 2048^3 (32 GiB) gas volumes at 3840x2160.
+    The DDA (texture residency + skip table: bare runs of hundreds of steps whose texel positions
+    are recovered from step counts) against the oracle on the very voxels resident on the device
+    (read back); ESVO, svo-rope and svo-naive on the GPU-built lossless tree of the same volume
+    (135 M / 366 M nodes, read back) against the oracle traversing that node array.  Sampled rows
+    of exterior, fly-over and interior frames of camera.txt."""
+    from xenodon_b200 import cameras
+    cams = cameras.camera_benchmark()
+    w, h = 3840, 2160
+    dims = (n, n, n)
+    frames = {"outside": cams[12], "over_the_top": cams[75], "inside": cams[120]}
+    rows = [(3, 2), (h // 2 - 1, 2), (h - 400, 2)]
+    ctx = xb.Context(0)
+    try:
+        ctx.synth_grid(xb.SYNTH_TNG, *dims)
+        assert ctx.grid_layout()[0] == xb.LAYOUT_TEXTURE
+        host = ctx.download_grid().data
+        assert host.shape == (n, n, n, 4)
+        ctx.set_target((0, 0, w, h))
+        ctx.set_params((1, 1, 1), dims, EMISSION)
+        for name, f in frames.items():
+            _rows_vs_oracle(xo, ctx, "dda", _cam(f), (w, h), rows, grid=host, tag=f"{n}^3 {name}")
+        if n == 1024:
+            # BASELINE config 5: the 8K frame over camera-rotate.txt
+            ctx.set_target((0, 0, 7680, 4320))
+            rot = cameras.camera_rotate()
+            _rows_vs_oracle(xo, ctx, "dda", _cam(rot[37]), (7680, 4320), [(2160, 1), (4000, 1)], grid=host, tag="8K")
+            ctx.set_target((0, 0, w, h))
+        del host
+        tree, stats, count, side = ctx.convert_resident_grid(chan_diff=0, type=xb.TYPE_ROPE, bind=True, want_nodes=True)
+        assert side == n and stats["depth"] == {1024: 10, 2048: 11}[n] and count == len(tree.nodes)
+        ctx.set_params((1, 1, 1), (side,) * 3, EMISSION)
+        for t in ("esvo", "svo-rope", "svo-naive"):
+            for name in ("outside", "inside"):
+                _rows_vs_oracle(xo, ctx, t, _cam(frames[name]), (w, h), rows[1:2], tree=tree, tag=f"{n}^3 {name}")
     finally:
         ctx.close()

@@ -33,6 +33,15 @@ def test_ingest_matches_libtiff_golden(xb):
         assert dims == (data.shape[2], data.shape[1], data.shape[0])
 
 
+def test_ingest_orientation_tag_matches_libtiff_golden(xb):
+    """The device decode applies the Orientation tag as libtiff does (rows / columns reversed)."""
+    z = np.load(os.path.join(GOLD, "tiff_orient_golden.npz"))
+    for name in z.files:
+        assert xb.tiff_stream_info(os.path.join(GOLD, name))["streamable"]
+        dims, dev = ingest(xb, os.path.join(GOLD, name))
+        assert np.array_equal(dev, z[name]), name
+
+
 VARIANTS = {
     "rgba_unassociated_strips": dict(spp=4, photometric=2, extra=2, rows_per_strip=3),
     "rgba_associated": dict(spp=4, photometric=2, extra=1),

@@ -272,6 +272,29 @@ def test_dda_resident_layouts_match_oracle(xb, xo, cam, dims, layout):
             assert image_diff(img, ref)[0] <= 1
 
 
+@pytest.mark.parametrize("dims", [(16384, 8, 8), (8, 12000, 6)])
+def test_dda_long_thin_grids_match_oracle(xb, xo, dims):
+    """Axes far longer than the benchmark volumes: the unchecked segments of the linear-layout
+    march bound their length with a slack that grows with the segment (rounding of the repeated
+    side-distance additions), so rays running the whole length of a 16384-voxel axis still visit
+    exactly the reference's voxels."""
+    rng = np.random.default_rng(dims[0] + dims[1])
+    g = random_grid(rng, *dims, sparsity=0.3)
+    long_axis = int(np.argmax(dims))
+    # cameras looking along the long axis from just outside and from inside; the output region is a
+    # small crop at the centre of a very wide display, so every ray stays within a fraction of a
+    # voxel per thousand steps of the axis and runs (nearly) the whole length of the grid
+    m = float(max(dims))
+    for off, fwd_sign in ((-0.02, 1.0), (1.02, -1.0), (0.4, 1.0)):
+        pos = [0.5 * d / m for d in dims]
+        pos[long_axis] = off
+        fwd = [0.00011, 0.00007, 0.00013]
+        fwd[long_axis] = fwd_sign
+        up = (0.0, 1.0, 0.0) if long_axis != 1 else (0.0, 0.0, 1.0)
+        _compare(xb, xo, "dda", grid=g, camera=(tuple(fwd), up, tuple(pos)), output=(32768 - 32, 18432 - 18, 64, 36),
+                 display=(0, 0, 65536, 36864), emission=2.0)
+
+
 def _skip_volume(xb, name, rng):
     if name == "blobs":  # large uniform blobs in a black box, ragged dimensions (partial edge bricks)
         return blobby_grid(rng, 70, 45, 61)

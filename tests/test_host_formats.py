@@ -71,6 +71,44 @@ def test_tiff_reader_matches_real_libtiff_golden(xb):
         assert np.array_equal(mine, z[name]), name  # bottom-up rows, premultiplied unassociated alpha
 
 
+def test_tiff_orientation_tag_matches_real_libtiff(xb):
+    """All eight values of the Orientation tag: libtiff's TIFFReadRGBAImage reverses rows for 1 / 5,
+    rows and columns for 2 / 6, columns for 3 / 7 and nothing for 4 / 8 (it never transposes);
+    fixtures written by tests/golden/make_golden.py from the real library."""
+    z = np.load(os.path.join(GOLD, "tiff_orient_golden.npz"))
+    assert len(z.files) == 8
+    seen = set()
+    for name in z.files:
+        got = xb.Grid.load_tiff(os.path.join(GOLD, name)).data
+        assert np.array_equal(got, z[name]), name
+        seen.add(got.tobytes())
+        info = xb.tiff_stream_info(os.path.join(GOLD, name))
+        o = int(name.split("_")[1].split(".")[0])
+        assert info["flip"] == (o in (1, 5, 2, 6)) and info["mirror"] == (o in (2, 6, 3, 7)), name
+    assert len(seen) == 4
+
+
+def test_tiff_with_crafted_dimensions_is_rejected_not_wrapped(xb, tmp_path):
+    """Width * height * 4 * layers must not wrap: a directory claiming 2^31 x 2^31 pixels (its strips
+    all pointing at the same few bytes) is refused with XN_ERR_LIMIT before any size is computed from it."""
+    def ifd(w, h):
+        out = bytearray(b"II*\x00\x08\x00\x00\x00")
+        tags = [(256, 4, w), (257, 4, h), (258, 3, 8), (259, 3, 1), (262, 3, 1), (273, 4, 8), (277, 3, 1),
+                (278, 4, h), (279, 4, 16)]
+        out += struct.pack("<H", len(tags))
+        for t, ty, v in tags:
+            out += struct.pack("<HHI", t, ty, 1) + (struct.pack("<I", v) if ty == 4 else struct.pack("<HH", v, 0))
+        out += struct.pack("<I", 0)
+        return bytes(out)
+    for w, h in ((0x80000000, 0x80000000), (0xFFFFFFFF, 3), (3, 0x80000000), (0x7FFFFFFF, 0x7FFFFFFF)):
+        p = tmp_path / f"crafted_{w}_{h}.tif"
+        p.write_bytes(ifd(w, h))
+        for call in (lambda: xb.Grid.load_tiff(p), lambda: xb.tiff_stream_info(p)):
+            with pytest.raises(xb.XenodonError) as e:
+                call()
+            assert e.value.status == -5, (w, h, str(e.value))  # XN_ERR_LIMIT
+
+
 def test_tiff_write_read_roundtrip_and_errors(xb, tmp_path):
     rng = np.random.default_rng(1)
     g = rng.integers(0, 256, (4, 6, 5, 4), dtype=np.uint8)
@@ -318,7 +356,7 @@ def test_ingest_plan_of_tiff_layouts(xb, tmp_path):
     write_tiff(p, layers, photometric=2, extra=2, rows_per_strip=5)
     info = xb.tiff_stream_info(p)
     assert info == {"streamable": True, "samples": 4, "photometric": 2, "has_alpha": True, "unassociated": True,
-                    "flip": True, "runs": 3}
+                    "flip": True, "mirror": False, "runs": 3}
     write_tiff(p, layers, photometric=2, extra=1, orientation=4)
     info = xb.tiff_stream_info(p)
     assert info["streamable"] and not info["unassociated"] and not info["flip"]

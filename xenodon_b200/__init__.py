@@ -238,7 +238,8 @@ def tiff_stream_info(path) -> dict:
     ok, fmt, runs = C.c_int(), (C.c_uint32 * 5)(), C.c_uint64()
     _check(lib().xn_tiff_stream_info(os.fsencode(path), C.byref(ok), fmt, C.byref(runs)))
     return {"streamable": bool(ok.value), "samples": fmt[0], "photometric": fmt[1], "has_alpha": bool(fmt[2]),
-            "unassociated": bool(fmt[3]), "flip": bool(fmt[4]), "runs": runs.value}
+            "unassociated": bool(fmt[3]), "flip": bool(fmt[4] & 1), "mirror": bool(fmt[4] & 2),
+            "runs": runs.value}
 
 
 def brick_layout(nx: int, ny: int, nz: int, top: int = -1) -> dict:

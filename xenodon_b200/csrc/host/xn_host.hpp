@@ -40,7 +40,7 @@ struct TiffSliceFormat { // identical for every slice of a plan that is `streama
     uint32_t samples;        // 1..4 bytes per pixel
     uint32_t photometric;    // 0 = white-is-zero, 1 = black-is-zero, 2 = RGB
     uint32_t has_alpha, unassociated;
-    uint32_t flip;           // file row r is grid row H - 1 - r
+    uint32_t flip;           // Orientation tag: bit 0 file row r is grid row H - 1 - r, bit 1 columns reversed too
 };
 struct TiffRun { // `bytes` contiguous file bytes at `offset`: whole rows in file order
     uint64_t offset, bytes;

@@ -207,6 +207,15 @@ TiffInfo check_dims(const std::vector<Directory>& dirs) {
     }
     // the reference counts layers in a uint16_t (Grid.cpp:35)
     if (depth > 65535) throw Error(XN_ERR_LIMIT, "TIFF: more than 65535 layers");
+    // libtiff's own limit on a raster is uint32 per axis; here the grid's byte size must also be
+    // representable, so that no later size computation (layer = W*H*4, layer*depth, strip and
+    // tile byte counts, all bounded by it) can wrap on a crafted file
+    uint64_t bytes = 0;
+    if (width > 0x7FFFFFFFull || height > 0x7FFFFFFFull || __builtin_mul_overflow(width, height, &bytes) ||
+        __builtin_mul_overflow(bytes, (uint64_t)4, &bytes) || __builtin_mul_overflow(bytes, depth, &bytes) ||
+        bytes > (1ull << 62))
+        throw Error(XN_ERR_LIMIT, "TIFF: volume of " + std::to_string(width) + "x" + std::to_string(height) + "x" +
+                                      std::to_string(depth) + " voxels is too large");
     return TiffInfo{width, height, depth};
 }
 
@@ -226,6 +235,20 @@ void alpha_rules(const Directory& d, bool& has_alpha, bool& unassociated) {
     }
 }
 
+// What TIFFReadRGBAImage does with the file's Orientation tag when asked for its default
+// bottom-left raster (libtiff tif_getimage.c, setorientation): bit 0 = rows are reversed, bit 1 =
+// columns are reversed.  Top-left / left-top (1, 5): rows; top-right / right-top (2, 6): both;
+// bottom-right / right-bottom (3, 7): columns; bottom-left / left-bottom (4, 8): neither.  (libtiff
+// does not transpose the 5-8 orientations either.)  Unknown values are read as the default, 1.
+uint32_t orientation_flips(uint64_t orientation) {
+    switch (orientation) {
+        case 2: case 6: return 3u;
+        case 3: case 7: return 2u;
+        case 4: case 8: return 0u;
+        default: return 1u;
+    }
+}
+
 void decode_directory(Reader& r, const Directory& d, uint8_t* out /* W*H*4, grid row order */) {
     if (d.compression != 1) throw Error(XN_ERR_FORMAT, "TIFF: only uncompressed data is supported");
     if (d.bits != 8) throw Error(XN_ERR_FORMAT, "TIFF: only 8 bits per sample are supported");
@@ -238,7 +261,8 @@ void decode_directory(Reader& r, const Directory& d, uint8_t* out /* W*H*4, grid
     const uint64_t colour_samples = rgb ? 3 : 1;
     bool has_alpha, unassociated;
     alpha_rules(d, has_alpha, unassociated);
-    const bool flip = d.orientation != 4; // bottom-left files are already in raster order
+    const uint32_t flips = orientation_flips(d.orientation);
+    const bool flip = (flips & 1u) != 0u, mirror = (flips & 2u) != 0u;
 
     auto put = [&](uint64_t x, uint64_t file_row, const uint8_t* px) {
         uint8_t rr, gg, bb, aa = 255;
@@ -257,7 +281,8 @@ void decode_directory(Reader& r, const Directory& d, uint8_t* out /* W*H*4, grid
             }
         }
         const uint64_t y = flip ? H - 1 - file_row : file_row;
-        uint8_t* o = out + 4 * (x + y * W);
+        const uint64_t xo = mirror ? W - 1 - x : x;
+        uint8_t* o = out + 4 * (xo + y * W);
         o[0] = rr; o[1] = gg; o[2] = bb; o[3] = aa;
     };
 
@@ -282,7 +307,10 @@ void decode_directory(Reader& r, const Directory& d, uint8_t* out /* W*H*4, grid
         if (d.tile_w == 0 || d.tile_h == 0) throw Error(XN_ERR_FORMAT, "TIFF: zero tile size");
         const uint64_t tx = (W + d.tile_w - 1) / d.tile_w, ty = (H + d.tile_h - 1) / d.tile_h;
         if (d.offsets.size() < tx * ty) throw Error(XN_ERR_FORMAT, "TIFF: missing tile offsets");
-        const uint64_t bytes = d.tile_w * d.tile_h * spp;
+        uint64_t bytes = 0;
+        if (d.tile_w > 0x7FFFFFFFull || d.tile_h > 0x7FFFFFFFull || __builtin_mul_overflow(d.tile_w, d.tile_h, &bytes) ||
+            __builtin_mul_overflow(bytes, spp, &bytes) || bytes > (1ull << 40))
+            throw Error(XN_ERR_LIMIT, "TIFF: tile size too large");
         buf.resize(bytes);
         for (uint64_t j = 0; j < ty; ++j)
             for (uint64_t i = 0; i < tx; ++i) {
@@ -342,7 +370,7 @@ TiffPlan tiff_plan(const std::string& path) {
         alpha_rules(d, has_alpha, unassociated);
         f.has_alpha = has_alpha;
         f.unassociated = unassociated;
-        f.flip = d.orientation != 4;
+        f.flip = orientation_flips(d.orientation);
         if (z == 0) plan.format = f;
         else if (std::memcmp(&f, &plan.format, sizeof f) != 0) plan.streamable = false;
         const uint64_t W = d.width, H = d.height;

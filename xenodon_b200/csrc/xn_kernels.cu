@@ -444,9 +444,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) dda_kernel(const __grid_constan
                 const int ry = sy > 0 ? (int)p.ny - 1 - py : py;
                 const int rz = sz > 0 ? (int)p.nz - 1 - pz : pz;
                 if (min(rx, min(ry, rz)) >= 4) {
+                    // slack: two steps, plus one per 2048 steps of the segment -- the rounding of the
+                    // repeated sd += td can drift by ~2^-25 N^2 td over N steps inside a binade, which
+                    // on axes of 8192 voxels and more would exceed a fixed slack
                     const float t_lim = fminf(
-                        t_end, fminf(sdx + (float)(rx - 2) * tdx,
-                                     fminf(sdy + (float)(ry - 2) * tdy, sdz + (float)(rz - 2) * tdz)));
+                        t_end, fminf(sdx + (float)(rx - 2 - (rx >> 11)) * tdx,
+                                     fminf(sdy + (float)(ry - 2 - (ry >> 11)) * tdy,
+                                           sdz + (float)(rz - 2 - (rz >> 11)) * tdz)));
                     if (t < t_lim) {
                         // One step advances t by at most td_min (the axis with the smallest
                         // spacing crosses a face within td_min), so while t < t_lim - 4 td_min four

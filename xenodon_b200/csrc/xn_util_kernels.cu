@@ -234,8 +234,9 @@ __global__ void tiff_decode_kernel(const uint8_t* __restrict__ raw, uint32_t* __
             g = (g * a + 127u) / 255u;
             b = (b * a + 127u) / 255u;
         }
-        const uint32_t y = f.flip ? H - 1u - row : row;
-        slice[(uint64_t)y * W + x] = r | (g << 8) | (b << 16) | (a << 24);
+        const uint32_t y = (f.flip & 1u) ? H - 1u - row : row;   // Orientation tag: rows reversed
+        const uint32_t xo = (f.flip & 2u) ? W - 1u - x : x;      // ... columns reversed
+        slice[(uint64_t)y * W + xo] = r | (g << 8) | (b << 16) | (a << 24);
     }
 }
 

@@ -1263,6 +1263,23 @@ __device__ __forceinline__ uint32_t df_hit_mask(const DfPlanes& q) {
 #endif
 }
 
+// Loop shape.  A node's hit children are consumed in two phases: a LEAF RUN (fetch the child's word;
+// a leaf adds colour * chord, ~20 instructions) that stops at the first internal child, and a NODE
+// STEP (enter that child, or return to the nearest ancestor with children left: corner, the twelve
+// plane parameters and -- when entering -- the eight slab tests, ~110 instructions).  Keeping the
+// two apart matters twice: a leaf child no longer pays (predicated off) for the plane arithmetic,
+// and the lanes of a warp reconverge after their leaf runs, so the expensive node step runs with
+// most of the warp instead of the few lanes that happened to need it in a given iteration
+// (ncu r01d: one 143-instruction body per child at 13.5 lanes, pop path at 6.3 lanes).
+#ifndef XN_DF_TWO_PHASE
+#define XN_DF_TWO_PHASE 1
+#endif
+#ifndef XN_DF_INLINE
+#define XN_DF_INLINE 0
+#endif
+#ifndef XN_DF_NODE_AT_A_TIME
+#define XN_DF_NODE_AT_A_TIME 1
+#endif
 template <bool STATS, bool STRICT, int LEVELS>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kernel(const __grid_constant__ FrameParams p) {
     __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS]; // [level][thread] = (node, todo | depth << 8)
@@ -1284,15 +1301,163 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
     const uint32_t stack = stack_base(stack_mem);
 
     DfPlanes q;
+
+#if XN_DF_NODE_AT_A_TIME
+    if (!STRICT) {
+        // Fast mode: the SET of leaves a ray adds (and every chord) is the shader's, but the order of
+        // the additions is free (the mode's contract is <= 1/255, not bit-identity).  That removes the
+        // return step altogether: on entering a node all of its hit leaf children are added at once
+        // (child index known at compile time: no plane selection; the chord t_max - max(t_min, 0)
+        // that decides the hit -- positive iff `t_min < t_max && t_max > 0` -- is the length added),
+        // and only the hit INTERNAL children are remembered.  Going back to an ancestor then needs
+        // its corner alone (to place the next internal child), not its planes -- so every iteration
+        // of the loop enters exactly one node, with the whole warp on the plane arithmetic.
+        for (;;) {
+            df_planes(P, side, rrd, bias, q);
+            const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.cnodes) + node));
+            const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.cnodes) + node) + 1);
+            const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            uint32_t inner = 0, hits = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < 8u; ++c) {
+                float t_min, t_max;
+                df_child(q, c, t_min, t_max);
+                const float chord = t_max - fmaxf(t_min, 0.0f);
+                if (chord > 0.0f) {
+                    if (STATS) ++hits;
+                    if (word_is_leaf(w[c])) {
+                        st.read(4); // color
+                        acc.add(w[c], chord);
+                    } else {
+                        inner |= 1u << c;
+                        if (c != 7u) st.read(4); // the shader's read on returning from this child (svo_df.comp:58)
+                    }
+                }
+            }
+            if (STATS) {
+                st.steps += 8;
+                st.read(32 + 4 * hits); // children[i] of every iteration + is_leaf_depth of the hit ones
+            }
+            // next node to enter: the first hit internal child, else the next one of the nearest
+            // ancestor that has any left
+            uint32_t c;
+            if (inner != 0u) {
+                c = (uint32_t)__ffs((int)inner) - 1u;
+                inner &= inner - 1u;
+                if (inner != 0u) {
+                    stack_store(stack, (uint32_t)min(sp, LEVELS - 1), node, inner | (depth << 8));
+                    ++sp;
+                }
+            } else {
+                if (sp == 0) break;
+                const uint2 e = stack_load(stack, (uint32_t)min(sp - 1, LEVELS - 1));
+                node = e.x;
+                uint32_t rest = e.y & 0xFFu;
+                depth = e.y >> 8;
+                c = (uint32_t)__ffs((int)rest) - 1u;
+                rest &= rest - 1u;
+                if (rest != 0u) stack_store(stack, (uint32_t)min(sp - 1, LEVELS - 1), node, rest | (depth << 8));
+                else --sp;
+                const float size = __int_as_float((127 - (int)depth) << 23); // exp2(-depth): the node's side
+                side = size * 0.5f;
+                const float rsize = pow2_reciprocal(size);
+                P = F3(size * floorf(P.x * rsize), size * floorf(P.y * rsize), size * floorf(P.z * rsize));
+            }
+            if (c & 4u) P.x += side;
+            if (c & 2u) P.y += side;
+            if (c & 1u) P.z += side;
+            node = load_word(p.cnodes, node, c);
+            ++depth;
+            side *= 0.5f;
+        }
+        store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
+        return;
+    }
+#endif
     df_planes(P, side, rrd, bias, q);
     uint32_t todo = df_hit_mask(q); // hit children of `node` not visited yet
     if (STATS) {
         st.steps += 8;
         st.read(32 + 4 * __popc(todo)); // children[i] of every iteration + is_leaf_depth of the hit ones
     }
-
+#if XN_DF_TWO_PHASE
     for (;;) {
-        if (todo == 0u) {
+        // leaf run: hit children in index order (the shader's accumulation order) up to the first
+        // internal one, whose word stays in `s`
+        uint32_t s = 0, c = 0;
+        bool internal = false;
+        while (todo != 0u && !internal) {
+            c = (uint32_t)__ffs((int)todo) - 1u;
+            todo &= todo - 1u;
+            s = load_word(p.cnodes, node, c);
+            if (word_is_leaf(s)) {
+                float t_min, t_max;
+                df_child(q, c, t_min, t_max);
+                st.read(4); // color
+                acc.add(s, t_max - fmaxf(t_min, 0.0f));
+            } else {
+                internal = true;
+            }
+        }
+        // node step
+        if (internal) {
+            // the shader pushes unless this is child 7 and pops when the subtree is done (one read of
+            // nodes[node].is_leaf_depth per pop, svo_df.comp:58)
+            if (c != 7u) st.read(4);
+            const f3 Pc = F3(P.x + ((c & 4u) ? side : 0.0f), P.y + ((c & 2u) ? side : 0.0f), P.z + ((c & 1u) ? side : 0.0f));
+            const float side_c = side * 0.5f;
+#if XN_DF_INLINE
+            // Most internal nodes a ray meets are parents of leaves only (7/8 of the internal nodes of
+            // a tree sit on its last level).  Such a child is consumed IN PLACE: its planes go to a
+            // second register set, its hit leaves are added, and the current node's state -- planes,
+            // children left -- is untouched, so there is no stack entry, no return step and no
+            // recomputation of the parent's planes.  Only when the child turns out to have an internal
+            // child of its own does the traversal really move into it (what has been added so far
+            // stays: the order of the shader's additions is kept).
+            DfPlanes q2;
+            df_planes(Pc, side_c, rrd, bias, q2);
+            uint32_t todo2 = df_hit_mask(q2);
+            if (STATS) {
+                st.steps += 8;
+                st.read(32 + 4 * __popc(todo2));
+            }
+            bool deep = false;
+            while (todo2 != 0u && !deep) {
+                const uint32_t c2 = (uint32_t)__ffs((int)todo2) - 1u;
+                const uint32_t w = load_word(p.cnodes, s, c2);
+                if (word_is_leaf(w)) {
+                    todo2 &= todo2 - 1u;
+                    float t_min, t_max;
+                    df_child(q2, c2, t_min, t_max);
+                    st.read(4); // color
+                    acc.add(w, t_max - fmaxf(t_min, 0.0f));
+                } else {
+                    deep = true; // c2 stays in todo2: the leaf run of the entered node meets it again
+                }
+            }
+            if (!deep) continue;
+            if (todo != 0u) {
+                stack_store(stack, (uint32_t)min(sp, LEVELS - 1), node, todo | (depth << 8));
+                ++sp;
+            }
+            P = Pc;
+            node = s;
+            ++depth;
+            side = side_c;
+            q = q2;
+            todo = todo2;
+            continue;
+#else
+            if (todo != 0u) {
+                stack_store(stack, (uint32_t)min(sp, LEVELS - 1), node, todo | (depth << 8));
+                ++sp;
+            }
+            P = Pc;
+            node = s;
+            ++depth;
+            side = side_c;
+#endif
+        } else {
             // node finished: back to the nearest ancestor with children left
             if (sp == 0) break;
             --sp;
@@ -1304,6 +1469,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
             side = size * 0.5f;
             // corner of the node: the corner of any descendant rounded down to a multiple of its size
             // (levels left by tail descents pushed nothing, so there is no per-level offset to undo)
+            const float rsize = pow2_reciprocal(size);
+            P = F3(size * floorf(P.x * rsize), size * floorf(P.y * rsize), size * floorf(P.z * rsize));
+        }
+        df_planes(P, side, rrd, bias, q);
+        if (internal) {
+            todo = df_hit_mask(q);
+            if (STATS) {
+                st.steps += 8;
+                st.read(32 + 4 * __popc(todo));
+            }
+        }
+    }
+#else
+    for (;;) {
+        if (todo == 0u) {
+            // node finished: back to the nearest ancestor with children left
+            if (sp == 0) break;
+            --sp;
+            const uint2 e = stack_load(stack, (uint32_t)min(sp, LEVELS - 1));
+            node = e.x;
+            todo = e.y & 0xFFu;
+            depth = e.y >> 8;
+            const float size = __int_as_float((127 - (int)depth) << 23); // exp2(-depth): the node's side
+            side = size * 0.5f;
             const float rsize = pow2_reciprocal(size);
             P = F3(size * floorf(P.x * rsize), size * floorf(P.y * rsize), size * floorf(P.z * rsize));
             df_planes(P, side, rrd, bias, q);
@@ -1318,9 +1507,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
             st.read(4); // color
             acc.add(s, t_max - fmaxf(t_min, 0.0f));
         } else {
-            // the shader pushes unless this is child 7 and pops when the subtree is done (one read of
-            // nodes[node].is_leaf_depth per pop, svo_df.comp:58); here the entry is only needed when
-            // hit children remain
             if (c != 7u) st.read(4);
             if (todo != 0u) {
                 stack_store(stack, (uint32_t)min(sp, LEVELS - 1), node, todo | (depth << 8));
@@ -1340,6 +1526,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
             }
         }
     }
+#endif
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
 }
 

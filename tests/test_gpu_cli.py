@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def run(xb, *args):
     r = subprocess.run([xb.CLI_PATH, *map(str, args)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0
-    return r.stdout
+    return r.stdout + r.stderr
 
 
 def test_render_headless_tiff_and_svo(xb, xo, tmp_path):

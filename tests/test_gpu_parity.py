@@ -371,6 +371,21 @@ def test_dda_bricked_gpu_convert_and_auto_policy(xb):
         ctx.close()
 
 
+@pytest.mark.parametrize("records", ["32", "64"])
+@pytest.mark.parametrize("cam", ["orbit", "inside", "oblique"])
+def test_rope_record_layouts_match_oracle(xb, xo, cam, records, monkeypatch):
+    """svo_rope has two residencies: 32-byte records (one sector per node: six ropes + colour, or
+    eight child words) for trees below 2^28 nodes and depth 16, and the 64-byte records otherwise.
+    XN_ROPE_RECORDS=64 forces the latter; both must reproduce the oracle bit for bit, with its
+    per-ray step and byte counts, on mixed-depth and on noisy trees."""
+    monkeypatch.setenv("XN_ROPE_RECORDS", records)
+    rng = np.random.default_rng(32 + len(cam))
+    for g in (blobby_grid(rng, 40, 29, 33), random_grid(rng, 16, 16, 16)):
+        tree, _ = xb.build_octree(xb.Grid(g), chan_diff=0, type=xb.TYPE_ROPE)
+        _compare(xb, xo, "svo-rope", tree=tree, camera=CAMERAS[cam], output=(0, 0, 160, 90), display=(0, 0, 160, 90),
+                 emission=2.0)
+
+
 def _deep_chain_tree(xb, depth, seed=9):
     """Hand-built octree `depth` levels deep: at every level one child (a different octant each
     time) is internal, the other seven are coloured leaves; node 0 = root, children by index."""

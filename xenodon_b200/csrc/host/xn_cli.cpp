@@ -21,6 +21,7 @@
 #include <sstream>
 #include <string>
 #include <string_view>
+#include <unordered_map>
 #include <vector>
 
 #include "xenodon_b200.h"
@@ -66,76 +67,71 @@ struct Logger {
     }
 } LOGGER;
 
-// ---- argument parsing with the reference's rules (src/core/arg_parse.cpp:7-84) ----
-using Action = std::function<bool(const char*)>;
-struct Flag {
-    bool* variable;
-    std::string long_arg;
-    int short_arg = -1;
-    bool seen = false;
-};
-struct Parameter {
-    Action action;
-    std::string value_name, long_arg;
-    int short_arg = -1;
-    bool seen = false;
-};
-struct Positional {
-    Action action;
-    std::string name;
-};
-struct Command {
-    std::vector<Flag> flags;
-    std::vector<Parameter> parameters;
-    std::vector<Positional> positional;
-};
+// ---- command-line table ----
+// One table per subcommand: switches (no value), options (one value) and operands, looked up by
+// spelling in a map built once.  The accepted spellings and the error texts are the reference's
+// command-line surface (src/core/arg_parse.cpp); the mechanism is this file's own.
+using Setter = std::function<bool(const char*)>;
+class ArgTable {
+    struct Entry {
+        std::string spelling; // "--quiet"
+        char letter;          // 'q' or 0
+        std::string value;    // name of the value for messages; empty for a switch
+        Setter set;           // switches: called with nullptr
+        bool used = false;
+        std::string shown() const { return letter ? spelling + "/-" + letter : spelling; }
+    };
+    std::vector<Entry> entries;
+    std::vector<std::pair<std::string, Setter>> operands;
 
-void parse_args(const std::vector<const char*>& args, Command& cmd) {
-    auto matches = [](std::string_view arg, const std::string& long_arg, int short_arg) {
-        return arg == long_arg || (arg.size() == 2 && short_arg != -1 && arg[1] == (char)short_arg);
-    };
-    auto duplicate = [](const char* type, const std::string& long_arg, int short_arg) {
-        std::string m = std::string("Duplicate specification of ") + type + " " + long_arg;
-        if (short_arg != -1) m += std::string("/-") + (char)short_arg;
-        return CliError(m);
-    };
-    size_t pos_seen = 0;
-    for (size_t i = 0; i < args.size(); ++i) {
-        const std::string_view arg = args[i];
-        if (!arg.empty() && arg[0] == '-') {
-            Flag* flag = nullptr;
-            for (auto& f : cmd.flags)
-                if (matches(arg, f.long_arg, f.short_arg)) { flag = &f; break; }
-            Parameter* param = nullptr;
-            if (!flag)
-                for (auto& p : cmd.parameters)
-                    if (matches(arg, p.long_arg, p.short_arg)) { param = &p; break; }
-            if (flag) {
-                if (flag->seen) throw duplicate("flag", flag->long_arg, flag->short_arg);
-                flag->seen = true;
-                *flag->variable = true;
-            } else if (param) {
-                ++i;
-                if (param->seen) throw duplicate("parameter", param->long_arg, param->short_arg);
-                if (i == args.size())
-                    throw CliError("Parameter " + std::string(arg) + " expects argument <" + param->value_name + ">");
-                param->seen = true;
-                if (!param->action(args[i]))
-                    throw CliError("Invalid value for <" + param->value_name + "> of parameter " + std::string(arg));
-            } else {
-                throw CliError("Unrecognized option " + std::string(arg));
-            }
-        } else if (pos_seen == cmd.positional.size()) {
-            throw CliError("Unexpected positional argument '" + std::string(arg) + "'");
-        } else {
-            auto& p = cmd.positional[pos_seen];
-            if (!p.action(args[i])) throw CliError("Invalid value for positional argument <" + p.name + ">");
-            ++pos_seen;
-        }
+public:
+    ArgTable& toggle(const char* spelling, char letter, bool* target) {
+        entries.push_back({spelling, letter, "", [target](const char*) { *target = true; return true; }});
+        return *this;
     }
-    if (pos_seen != cmd.positional.size())
-        throw CliError("Missing required positional argument <" + cmd.positional[pos_seen].name + ">");
-}
+    ArgTable& option(const char* spelling, char letter, const char* value, Setter set) {
+        entries.push_back({spelling, letter, value, std::move(set)});
+        return *this;
+    }
+    ArgTable& operand(const char* name, Setter set) {
+        operands.emplace_back(name, std::move(set));
+        return *this;
+    }
+    void apply(const std::vector<const char*>& words) {
+        std::unordered_map<std::string, Entry*> by_spelling;
+        for (auto& e : entries) {
+            by_spelling[e.spelling] = &e;
+            if (e.letter) by_spelling[std::string("-") + e.letter] = &e;
+        }
+        size_t next_operand = 0;
+        for (auto w = words.begin(); w != words.end(); ++w) {
+            const std::string word = *w;
+            if (word.empty() || word[0] != '-') {
+                if (next_operand == operands.size()) throw CliError("Unexpected positional argument '" + word + "'");
+                auto& [name, set] = operands[next_operand++];
+                if (!set(*w)) throw CliError("Invalid value for positional argument <" + name + ">");
+                continue;
+            }
+            const auto hit = by_spelling.find(word);
+            if (hit == by_spelling.end()) throw CliError("Unrecognized option " + word);
+            Entry& e = *hit->second;
+            const bool takes_value = !e.value.empty();
+            if (e.used)
+                throw CliError(std::string("Duplicate specification of ") + (takes_value ? "parameter " : "flag ") + e.shown());
+            e.used = true;
+            if (!takes_value) {
+                e.set(nullptr);
+            } else if (++w == words.end()) {
+                throw CliError("Parameter " + word + " expects argument <" + e.value + ">");
+            } else if (!e.set(*w)) {
+                throw CliError("Invalid value for <" + e.value + "> of parameter " + word);
+            }
+        }
+        if (next_operand != operands.size())
+            throw CliError("Missing required positional argument <" + operands[next_operand].first + ">");
+    }
+};
+using Action = Setter;
 
 // digits, '.' and '-' only (no exponent), src/core/arg_parse.h:75-100
 template <typename T>
@@ -357,24 +353,24 @@ Action voxel_ratio_opt(float* var) {
 
 RenderOptions parse_render_args(const std::vector<const char*>& args) {
     RenderOptions o;
-    Command cmd;
-    cmd.flags = {{&o.quiet, "--quiet", 'q'}, {&o.xorg, "--xorg"}, {&o.discard_output, "--discard-output"}};
-    cmd.parameters = {
-        {string_opt(&o.log_output), "output path", "--log-output"},
-        {string_opt(&o.headless), "config path", "--headless"},
-        {string_opt(&o.output), "output path", "--output"},
-        {string_opt(&o.direct), "config path", "--direct"},
-        {string_opt(&o.xorg_multi_gpu), "config path", "--xorg-multi-gpu"},
-        {float_min_opt<float>(&o.emission, 0.f), "emission coefficient", "--emission-coeff", 'e'},
-        {string_opt(&o.volume_type), "volume type", "--volume-type"},
-        {string_opt(&o.shader), "shader", "--shader", 's'},
-        {voxel_ratio_opt(o.voxel_ratio), "voxel dimension ratio", "--voxel-ratio", 'r'},
-        {string_opt(&o.stats_path), "stats output", "--stats-output"},
-        {string_opt(&o.camera), "camera", "--camera"},
-        {int_range_opt<size_t>(&o.repeat, 0, std::numeric_limits<size_t>::max()), "frame repeat", "--repeat"},
-    };
-    cmd.positional = {{string_opt(&o.volume_path), "volume path"}};
-    parse_args(args, cmd);
+    ArgTable()
+        .toggle("--quiet", 'q', &o.quiet)
+        .toggle("--xorg", 0, &o.xorg)
+        .toggle("--discard-output", 0, &o.discard_output)
+        .option("--log-output", 0, "output path", string_opt(&o.log_output))
+        .option("--headless", 0, "config path", string_opt(&o.headless))
+        .option("--output", 0, "output path", string_opt(&o.output))
+        .option("--direct", 0, "config path", string_opt(&o.direct))
+        .option("--xorg-multi-gpu", 0, "config path", string_opt(&o.xorg_multi_gpu))
+        .option("--emission-coeff", 'e', "emission coefficient", float_min_opt<float>(&o.emission, 0.f))
+        .option("--volume-type", 0, "volume type", string_opt(&o.volume_type))
+        .option("--shader", 's', "shader", string_opt(&o.shader))
+        .option("--voxel-ratio", 'r', "voxel dimension ratio", voxel_ratio_opt(o.voxel_ratio))
+        .option("--stats-output", 0, "stats output", string_opt(&o.stats_path))
+        .option("--camera", 0, "camera", string_opt(&o.camera))
+        .option("--repeat", 0, "frame repeat", int_range_opt<size_t>(&o.repeat, 0, std::numeric_limits<size_t>::max()))
+        .operand("volume path", string_opt(&o.volume_path))
+        .apply(args);
 
     const int backends = (int)o.xorg + (int)!o.headless.empty() + (int)!o.direct.empty();
     if (backends == 0) throw CliError("Missing required backend --xorg, --headless or --direct");
@@ -679,13 +675,16 @@ void convert(const std::vector<const char*>& args) {
     bool dag = false, rope = false, host_only = false;
     int channel_difference = -1;
     double stddev = -1;
-    Command cmd;
-    cmd.flags = {{&dag, "--dag"}, {&rope, "--rope"}, {&host_only, "--host"}};
-    cmd.parameters = {{int_range_opt<int>(&channel_difference, 0, 255), "channel difference", "--chan-diff"},
-                      {float_min_opt<double>(&stddev, 0.0), "std. dev", "--std-dev"}};
-    cmd.positional = {{string_opt(&src), "source tiff path"}, {string_opt(&dst), "destination svo path"}};
+    ArgTable table;
+    table.toggle("--dag", 0, &dag)
+        .toggle("--rope", 0, &rope)
+        .toggle("--host", 0, &host_only)
+        .option("--chan-diff", 0, "channel difference", int_range_opt<int>(&channel_difference, 0, 255))
+        .option("--std-dev", 0, "std. dev", float_min_opt<double>(&stddev, 0.0))
+        .operand("source tiff path", string_opt(&src))
+        .operand("destination svo path", string_opt(&dst));
     try {
-        parse_args(args, cmd);
+        table.apply(args);
     } catch (const CliError& e) {
         std::printf("Error: %s\n", e.what());
         return;
@@ -709,6 +708,13 @@ void convert(const std::vector<const char*>& args) {
     const uint64_t voxels = dims[0] * dims[1] * dims[2];
     std::printf("%llux%llux%llu = %llu pixels\n", (unsigned long long)dims[0], (unsigned long long)dims[1],
                 (unsigned long long)dims[2], (unsigned long long)voxels);
+    // the reference's report (src/convert.cpp:66-71); memory_footprint() = sizeof(Grid) + voxels * 4,
+    // sizeof(Grid) = sizeof(Octree) = 32 on x86-64 (src/model/Grid.h:62-64, Octree.h:66-68)
+    constexpr unsigned long long OBJECT_BYTES = 32;
+    std::printf("Source grid:\n Dimensions: %llux%llux%llu\n Size: %llu bytes\n", (unsigned long long)dims[0],
+                (unsigned long long)dims[1], (unsigned long long)dims[2], OBJECT_BYTES + (unsigned long long)(voxels * 4));
+    std::printf("Converting to octree...\n");
+    std::fflush(stdout);
     xn_node* nodes = nullptr;
     uint64_t count = 0, side = 0;
     xn_build_stats st{};
@@ -723,13 +729,8 @@ void convert(const std::vector<const char*>& args) {
         xn_ctx* ctx = nullptr;
         if (xn_ctx_create(0, &ctx) == XN_OK) {
             xn_set_grid_layout(ctx, XN_GRID_LAYOUT_LINEAR); // the builder reads the x-major copy
-            if (xn_upload_grid_tiff(ctx, src.c_str(), nullptr, nullptr) == XN_OK) {
-                std::printf("Source grid:\n Dimensions: %llux%llux%llu\n Size: %llu bytes\n", (unsigned long long)dims[0],
-                            (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)(voxels * 4));
-                std::printf("Converting to octree...\n");
-                std::fflush(stdout);
+            if (xn_upload_grid_tiff(ctx, src.c_str(), nullptr, nullptr) == XN_OK)
                 rc = xn_convert_resident_grid(ctx, std::max(channel_difference, 0), type, 0, &nodes, &count, &side, &st);
-            }
             xn_ctx_destroy(ctx);
             on_gpu = rc == XN_OK;
         }
@@ -740,21 +741,16 @@ void convert(const std::vector<const char*>& args) {
             std::printf("Error reading '%s': %s\n", src.c_str(), xn_last_error());
             return;
         }
-        std::printf("Source grid:\n Dimensions: %llux%llux%llu\n Size: %llu bytes\n", (unsigned long long)dims[0],
-                    (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)(voxels * 4));
-        std::printf("Converting to octree...\n");
-        std::fflush(stdout);
-    }
-    if (!on_gpu)
         rc = stddev >= 0
                  ? xn_build_octree(grid.data(), dims[0], dims[1], dims[2], 1, stddev, type, &nodes, &count, &side, &st)
                  : xn_build_octree(grid.data(), dims[0], dims[1], dims[2], 0, (double)std::max(channel_difference, 0),
                                    type, &nodes, &count, &side, &st);
+    }
     if (rc != XN_OK) {
         std::printf("Error: %s\n", xn_last_error());
         return;
     }
-    std::printf("Built on the %s\n", on_gpu ? "GPU" : "host");
+    std::fprintf(stderr, "Built on the %s\n", on_gpu ? "GPU" : "host"); // not part of the reference's report
     {
         // same arithmetic as the reference's report (src/convert.cpp:86-111), quirks included
         auto ipow = [](size_t x, size_t y) {
@@ -768,7 +764,7 @@ void convert(const std::vector<const char*>& args) {
         std::printf("Generated octree:\n");
         std::printf(" Dimensions: %llux%llux%llu\n", (unsigned long long)side, (unsigned long long)side,
                     (unsigned long long)side);
-        std::printf(" Size: %llu bytes\n", (unsigned long long)(count * sizeof(xn_node)));
+        std::printf(" Size: %llu bytes\n", OBJECT_BYTES + (unsigned long long)(count * sizeof(xn_node)));
         std::printf(" Perfect tree nodes: %llu\n", (unsigned long long)perfect);
         std::printf(" Total nodes: %llu (%.5f%%)\n", (unsigned long long)st.total_nodes, total_prop * 100);
         std::printf(" Unique nodes: %llu (%.5f%%)\n", (unsigned long long)count, unique_prop * 100);

@@ -102,7 +102,8 @@ struct xn_ctx {
     cudaTextureObject_t tex_unorm = 0, tex_raw = 0;
     int layout_mode = XN_GRID_LAYOUT_AUTO;
     uint64_t nx = 0, ny = 0, nz = 0;
-    xn::DNode* nodes = nullptr;  // file-order 64-byte records (svo_rope)
+    xn::DNode* nodes = nullptr;  // file-order 64-byte records (svo_rope on trees beyond the RNode limits)
+    xn::RNode* rnodes = nullptr; // file-order 32-byte rope records (svo_rope); exactly one of the two is resident
     xn::CNode* cnodes = nullptr; // compact level-order records of the internal nodes (the other three)
     uint32_t* top_table = nullptr; // svo_naive entry table
     uint32_t top_levels = 0;
@@ -111,6 +112,7 @@ struct xn_ctx {
     bool grid_has_black_background = false;
     uint4* skip_table = nullptr; // DDA skip table of the resident grid (any layout)
     uint32_t skip_dim[3] = {0, 0, 0}, skip_shift = 0;
+    double skip_uniform = 0.0; // share of the grid's bricks that hold one colour
 
     // target
     xn_rect output{0, 0, 0, 0}, display{0, 0, 0, 0};
@@ -148,8 +150,11 @@ struct xn_ctx {
         nx = ny = nz = 0;
     }
     bool have_grid() const { return grid || bricks || tex_array; }
+    bool have_svo() const { return nodes || rnodes; }
     void free_nodes() {
         if (nodes) cudaFree(nodes);
+        if (rnodes) cudaFree(rnodes);
+        rnodes = nullptr;
         if (cnodes) cudaFree(cnodes);
         if (top_table) cudaFree(top_table);
         nodes = nullptr;
@@ -174,7 +179,7 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     if (traversal == XN_DDA) {
         if (!ctx->have_grid())
             throw xn::Error(XN_ERR_INVALID, "Shader 'dda' is incompatible with model type 'svo' (requires 'tiff')");
-    } else if (!ctx->nodes) {
+    } else if (!ctx->have_svo()) {
         throw xn::Error(XN_ERR_INVALID, std::string("Shader '") + TRAVERSAL_NAMES[traversal] +
                                             "' is incompatible with model type 'tiff' (requires 'svo')");
     }
@@ -223,6 +228,7 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.ny = (uint32_t)ctx->ny;
     p.nz = (uint32_t)ctx->nz;
     p.nodes = ctx->nodes;
+    p.rnodes = ctx->rnodes;
     p.cnodes = ctx->cnodes;
     p.top_table = ctx->top_table;
     p.top_levels = ctx->top_levels;
@@ -259,7 +265,7 @@ void classify_grid(xn_ctx* ctx) {
     if (const char* s = std::getenv("XN_SKIP_CAP")) cap = (uint32_t)std::strtoul(s, nullptr, 10);
     if (ctx->nx > 0x7FFFFFu || ctx->ny > 0x7FFFFFu || ctx->nz > 0x7FFFFFu) return; // texel centres exact below 2^23
     e = xn::build_skip_table(ctx->grid, (uint32_t)ctx->nx, (uint32_t)ctx->ny, (uint32_t)ctx->nz, shift, cap,
-                             &ctx->skip_table, ctx->skip_dim, ctx->stream);
+                             &ctx->skip_table, ctx->skip_dim, &ctx->skip_uniform, ctx->stream);
     if (e != cudaSuccess) {
         // the table only saves fetches: without it the march reads every texel
         cudaGetLastError();
@@ -298,7 +304,13 @@ int wanted_layout(const xn_ctx* ctx, xn::BrickLayout& L) {
     }
     uint64_t min_voxels = 1ull << 29;
     if (const char* e = std::getenv("XN_TEXTURE_MIN_VOXELS")) min_voxels = std::strtoull(e, nullptr, 10);
-    return tex_ok && voxels >= min_voxels ? XN_GRID_LAYOUT_TEXTURE : XN_GRID_LAYOUT_LINEAR;
+    if (tex_ok && voxels >= min_voxels) return XN_GRID_LAYOUT_TEXTURE;
+    // Smaller volumes are bound by the texture unit's rate there (one quad per clock per SM) and stay
+    // linear -- unless the skip table makes most fetches unnecessary: with half of the bricks
+    // uniform the texture-path march with the table wins (bunny-shape 512x361x512: 6766 vs 5595
+    // Mrays/s on config 1, 3038 vs 2216 on the config 2 path)
+    if (tex_ok && ctx->skip_table && ctx->skip_uniform >= 0.5 && voxels >= (1ull << 24)) return XN_GRID_LAYOUT_TEXTURE;
+    return XN_GRID_LAYOUT_LINEAR;
 }
 
 cudaMemcpy3DParms array_copy_parms(xn_ctx* ctx, bool to_array) {
@@ -435,11 +447,26 @@ void apply_l2_window(xn_ctx* ctx) {
 void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) {
     // d_raw: count 40-byte nodes on the device; produce the 64-byte resident layout
     ctx->free_nodes();
-    XN_CUDA(cudaMalloc(&ctx->nodes, count * sizeof(xn::DNode)));
     uint32_t* d_max = nullptr;
     XN_CUDA(cudaMalloc(&d_max, sizeof(uint32_t)));
     XN_CUDA(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), ctx->stream));
-    XN_CUDA(xn::launch_relayout(d_raw, count, ctx->nodes, d_max, ctx->stream));
+    XN_CUDA(xn::launch_max_depth(d_raw, count, d_max, ctx->stream));
+    uint32_t maxd = 0;
+    XN_CUDA(cudaMemcpyAsync(&maxd, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    XN_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_max);
+    if (maxd > 23) throw xn::Error(XN_ERR_LIMIT, "octree deeper than 23 levels (the traversal stack depth of the reference)");
+    // svo_rope reads 32-byte records when the tree fits their fields (index 28 bits, depth 4 bits),
+    // else the 64-byte ones; XN_ROPE_RECORDS=64 forces the latter (A/B runs, tests of both)
+    const char* rr = std::getenv("XN_ROPE_RECORDS");
+    const bool small_records = count < xn::RNODE_MAX_NODES && maxd <= xn::RNODE_MAX_DEPTH && !(rr && std::strcmp(rr, "64") == 0);
+    if (small_records) {
+        XN_CUDA(cudaMalloc(&ctx->rnodes, count * sizeof(xn::RNode)));
+        XN_CUDA(xn::launch_relayout_rnodes(d_raw, count, ctx->rnodes, ctx->stream));
+    } else {
+        XN_CUDA(cudaMalloc(&ctx->nodes, count * sizeof(xn::DNode)));
+        XN_CUDA(xn::launch_relayout(d_raw, count, ctx->nodes, ctx->stream));
+    }
     {
         const cudaError_t e = xn::build_compact_nodes(d_raw, count, &ctx->cnodes, &ctx->internal_count, ctx->stream);
         if (e == cudaErrorInvalidValue) {
@@ -451,14 +478,7 @@ void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) 
     }
     uint32_t root[2] = {0, 0};
     XN_CUDA(cudaMemcpyAsync(root, (const uint8_t*)d_raw + 32, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    uint32_t maxd = 0;
-    XN_CUDA(cudaMemcpyAsync(&maxd, d_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
     XN_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_max);
-    if (maxd > 23) {
-        ctx->free_nodes();
-        throw xn::Error(XN_ERR_LIMIT, "octree deeper than 23 levels (the traversal stack depth of the reference)");
-    }
     apply_l2_window(ctx);
     ctx->root_meta = xn::make_meta(root[0], root[1]);
     // svo_naive entry table over the first min(tree depth, TOP_LEVELS_MAX) levels

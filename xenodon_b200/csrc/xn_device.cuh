@@ -39,6 +39,22 @@ struct __align__(32) CNode {
 };
 static_assert(sizeof(CNode) == 32, "compact node must be 32 bytes");
 
+// Rope-tree residency read by svo_rope when the tree allows it (fewer than 2^28 nodes, depth <= 15):
+// every node of the file, 32 bytes (one sector) each, in file order.
+//   internal node : w[c] = child index | child_is_leaf << 31   (a child's depth is its parent's + 1)
+//   leaf node     : w[0..5] = the six ropes, neighbour index | neighbour depth << 28 (0 = no
+//                   neighbour, as in the file); w[6] = rgb | own depth << 24; w[7] = RNODE_LEAF_TAG
+// A ray leaving a leaf needs that leaf's colour and ONE of its ropes: both sit in the one sector
+// the visit fetches, where the 64-byte DNode spreads the six (rope, neighbour meta) pairs over two
+// sectors that different rays touch -- half the DRAM traffic per touched leaf.
+struct __align__(32) RNode {
+    uint32_t w[8];
+};
+static_assert(sizeof(RNode) == 32, "rope node must be 32 bytes");
+constexpr uint32_t RNODE_LEAF_TAG = 0xFFFFFFFFu;
+constexpr uint64_t RNODE_MAX_NODES = 1ull << 28;
+constexpr uint32_t RNODE_MAX_DEPTH = 15;
+
 // svo_naive entry table: at most this many levels of the tree are folded into it (8: 64 MiB)
 #ifndef XN_TOP_LEVELS_MAX
 #define XN_TOP_LEVELS_MAX 8
@@ -84,6 +100,7 @@ struct FrameParams {
     const uint4* skip_table;
     uint32_t skip_dim[3], skip_shift;
     const DNode* nodes;   // svo_rope (and the file-order view of the tree)
+    const RNode* rnodes;  // svo_rope, 32-byte records (nullptr: the tree exceeds their limits, nodes is read)
     const CNode* cnodes;  // svo_naive, svo_df, esvo
     // svo_naive: what find() reaches after its first top_levels levels, for each of the
     // 2^(3 top_levels) aligned cells of the cube (a leaf word, or the word offset of an internal

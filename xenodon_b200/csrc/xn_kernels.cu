@@ -807,12 +807,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         const float td_min = fminf(tdx, fminf(tdy, tdz));
         const float td45 = 4.5f * td_min;
         const float td_look = 8.0f * td_min;                    // spacing floor of table look-ups (two trips)
-        const float inv_trip = 1.0f / (4.00390625f * td_min);  // trips per unit of t, rounded down a little
+        const float inv_trip = 0.999999f / (4.00390625f * td_min); // trips per unit of t, rounded down a little
         const float itdx = 1.0f / tdx, itdy = 1.0f / tdy, itdz = 1.0f / tdz;
         // longest bare run, in trips minus one: an axis' side distance takes at most 4 n + 1 additions in
         // n trips, each rounded by at most 2^-24 (t_end + td_i), so the step count recovered from it is
         // off by less than (4 n + 1) 2^-24 (t_end / td_min + 1) -- kept below a quarter
-        const float n_cap = fminf(1022.0f, fmaxf(65536.0f * td_min / ((t_max - fmaxf(t_min, 0.0f)) + td_min) * 15.9f - 2.0f, 0.0f));
+        const uint32_t n_cap = (uint32_t)fminf(1023.0f, fmaxf(65536.0f * td_min / ((t_max - fmaxf(t_min, 0.0f)) + td_min) * 15.9f - 1.0f, 0.0f));
         float t_safe = -1.0f; // a step that ends before t_safe lands on a texel of colour uc
         float t_look = 0.0f;  // consult the table at the first trip boundary at or after this time
         texel uct = TF::zero(); // uc as a texel (strict mode)
@@ -906,8 +906,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         const unsigned am = __activemask();                                                         \
         if (__any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                                      \
         if (!STRICT && XN_SKIP_BARE) {                                                              \
-            const float x = ((fminf(t_safe, t_end) - td45) - t) * inv_trip;                         \
-            uint32_t ni = (pf == 0.0f && x > 0.0f) ? (uint32_t)fminf(x * 0.999999f, n_cap) + 1u : 0u; \
+            /* trips certain to be known: the k-th starts before t + 4 k td_min (1 + 2^-10), and must  */ \
+            /* start before min(t_safe, t_end) - 4.5 td_min; +1 because trip 0 starts at t itself; a */ \
+            /* negative count converts to 0                                                          */ \
+            const float x = __fmaf_rn(fminf(t_safe - td45, t_lim4) - t, inv_trip, 1.0f);              \
+            const uint32_t ni = pf == 0.0f ? min(__float2uint_rz(x), n_cap) : 0u;                     \
             const uint32_t n = __reduce_min_sync(am, ni);                                           \
             if (n != 0u) {                                                                          \
                 /* positions are not needed while nothing is fetched: the run advances the side */  \
@@ -1840,6 +1843,136 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_rope_ker
 }
 
 // ---------------------------------------------------------------------------------
+// svo_rope over the 32-byte rope records (RNode, xn_device.cuh): the same walk, same arithmetic,
+// same per-ray read counts as svo_rope_kernel; what differs is where a node's words live.  A visit
+// to a leaf fetches its ONE sector as two 128-bit loads: colour (w[6]) and all six ropes, of which
+// the exit face picks one.  The record a rope leads to is fetched whole as well; its tag word says
+// whether it is the next leaf or an internal node to descend through (child words carry the
+// child's leaf flag, so every further level is again one record fetch).
+// ---------------------------------------------------------------------------------
+struct RRec {
+    uint4 a, b; // w[0..3], w[4..7]
+};
+__device__ __forceinline__ RRec load_rrec(const RNode* __restrict__ nodes, uint32_t i) {
+    const uint4* q = reinterpret_cast<const uint4*>(nodes + i);
+    RRec r;
+    r.a = __ldg(q);
+    r.b = __ldg(q + 1);
+    return r;
+}
+__device__ __forceinline__ uint32_t rrec_word(const RRec& r, uint32_t k) { // k in 0..7, runtime
+    const uint32_t lo = (k & 2u) ? ((k & 1u) ? r.a.w : r.a.z) : ((k & 1u) ? r.a.y : r.a.x);
+    const uint32_t hi = (k & 2u) ? ((k & 1u) ? r.b.w : r.b.z) : ((k & 1u) ? r.b.y : r.b.x);
+    return (k & 4u) ? hi : lo;
+}
+// find() / find_relative() loop body (svo_rope.comp:14-26, :33-47) from record `rec` of node `node`
+// at `offset` / `extent`, down to the leaf containing pos; returns with the leaf's record in `rec`
+template <bool STATS>
+__device__ __forceinline__ void descend_rrec(const RNode* __restrict__ nodes, f3 pos, uint32_t& node, RRec& rec,
+                                             f3& offset, float& extent, RayStats<STATS>& st) {
+    bool leaf = rec.b.w == RNODE_LEAF_TAG;
+    for (;;) {
+        st.read(4); // is_leaf_depth
+        if (leaf) return;
+        extent *= 0.5f;
+        uint32_t child;
+        {
+            const float cx = offset.x + extent, cy = offset.y + extent, cz = offset.z + extent;
+            asm("{\n\t"
+                ".reg .f32 fx, fy, fz, mf;\n\t"
+                "set.ge.f32.f32 fx, %4, %7;\n\t"
+                "set.ge.f32.f32 fy, %5, %8;\n\t"
+                "set.ge.f32.f32 fz, %6, %9;\n\t"
+                "fma.rn.f32 %1, fx, %10, %1;\n\t"
+                "fma.rn.f32 %2, fy, %10, %2;\n\t"
+                "fma.rn.f32 %3, fz, %10, %3;\n\t"
+                "fma.rn.f32 mf, fx, 0f40800000, fz;\n\t"
+                "fma.rn.f32 mf, fy, 0f40000000, mf;\n\t"
+                "cvt.rzi.u32.f32 %0, mf;\n\t"
+                "}"
+                : "=r"(child), "+f"(offset.x), "+f"(offset.y), "+f"(offset.z)
+                : "f"(pos.x), "f"(pos.y), "f"(pos.z), "f"(cx), "f"(cy), "f"(cz), "f"(extent));
+        }
+        st.read(4); // children[child]
+        const uint32_t w = rrec_word(rec, child);
+        node = w & 0x7FFFFFFFu;
+        leaf = (w >> 31) != 0u;
+        rec = load_rrec(nodes, node);
+    }
+}
+
+template <bool STATS, bool STRICT>
+__global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_rope32_kernel(const __grid_constant__ FrameParams p) {
+    uint32_t ix, iy;
+    thread_pixel(p, ix, iy);
+    if (ix >= p.out_w || iy >= p.out_h) return;
+    RayStats<STATS> st;
+
+    const f3 rd = make_ray(p, p.out_x + (int32_t)ix, p.out_y + (int32_t)iy);
+    const f3 ro = F3(p.pos[0], p.pos[1], p.pos[2]);
+
+    f3 sgn = F3(gsign(rd.x), gsign(rd.y), gsign(rd.z));
+    const uint32_t nbx = 1u - (uint32_t)gmax(sgn.x, 0.0f);
+    const uint32_t nby = 3u - (uint32_t)gmax(sgn.y, 0.0f);
+    const uint32_t nbz = 5u - (uint32_t)gmax(sgn.z, 0.0f);
+    sgn = F3(sgn.x + 0.1f, sgn.y + 0.1f, sgn.z + 0.1f);
+
+    const f3 rrd = F3(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+    const f3 bias = F3(rrd.x * ro.x, rrd.y * ro.y, rrd.z * ro.z);
+    const RNode* __restrict__ nodes = p.rnodes;
+
+    Accum<STRICT> acc;
+    float t_min, t_max;
+    if (unit_cube_slab(rrd, bias, t_min, t_max)) {
+        f3 pos = F3(ro.x + t_min * rd.x, ro.y + t_min * rd.y, ro.z + t_min * rd.z);
+        uint32_t node = 0;
+        f3 offset = F3(0.f, 0.f, 0.f);
+        float side = 1.0f;
+        RRec rec = load_rrec(nodes, 0u);
+        descend_rrec(nodes, pos, node, rec, offset, side, st);
+
+        for (;;) {
+            float u_min, u_max;
+            f3 far;
+            node_slab(offset, side, rrd, bias, u_min, u_max, far);
+            const float step = u_max - (XN_SLAB_FMNMX ? fmaxf(u_min, 0.0f) : gmax(u_min, 0.0f));
+            st.read(4); // color
+            acc.add(rec.b.z, step);
+            st.step();
+
+            // neighbor_index, svo_rope.comp:50-63 (ties go to the later axis): the three candidate
+            // ropes of this ray are fixed by its signs
+            uint32_t r;
+            if (far.x < fminf(far.y, far.z)) {
+                r = nbx ? rec.a.y : rec.a.x;
+                offset.x += sgn.x * side;
+            } else if (far.y < far.z) {
+                r = nby == 3u ? rec.a.w : rec.a.z;
+                offset.y += sgn.y * side;
+            } else {
+                r = nbz == 5u ? rec.b.y : rec.b.x;
+                offset.z += sgn.z * side;
+            }
+            st.read(4); // rope
+            if (r == 0u) break;
+            node = r & 0x0FFFFFFFu;
+            rec = load_rrec(nodes, node);
+
+            // find_relative, svo_rope.comp:29-48
+            pos = F3(ro.x + u_max * rd.x, ro.y + u_max * rd.y, ro.z + u_max * rd.z);
+            side = __int_as_float((127 - (int)(r >> 28)) << 23); // exp2(-depth of the neighbour)
+            const float rside = pow2_reciprocal(side);
+            // offset -= mod(offset, side) as side * floor(offset / side) (exact, see svo_rope_kernel)
+            offset.x = side * floorf(offset.x * rside);
+            offset.y = side * floorf(offset.y * rside);
+            offset.z = side * floorf(offset.z * rside);
+            descend_rrec(nodes, pos, node, rec, offset, side, st);
+        }
+    }
+    store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
+}
+
+// ---------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------
 static bool force_idx64() {
@@ -1886,7 +2019,10 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
             if (deep) svo_df_kernel<STATS, STRICT, 24><<<grid, block, 0, stream>>>(p);
             else svo_df_kernel<STATS, STRICT, 12><<<grid, block, 0, stream>>>(p);
             break;
-        case 4: svo_rope_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p); break;
+        case 4:
+            if (p.rnodes) svo_rope32_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p);
+            else svo_rope_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p);
+            break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

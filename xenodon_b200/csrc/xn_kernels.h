@@ -7,7 +7,10 @@
 
 namespace xn {
 cudaError_t launch_traversal(int traversal, const FrameParams& p, bool stats, bool strict, cudaStream_t stream);
-cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth, cudaStream_t stream);
+cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, cudaStream_t stream);
+cudaError_t launch_max_depth(const void* raw40, uint64_t count, uint32_t* d_max_depth, cudaStream_t stream);
+// 32-byte rope records (RNode): the caller checks RNODE_MAX_NODES / RNODE_MAX_DEPTH first
+cudaError_t launch_relayout_rnodes(const void* raw40, uint64_t count, RNode* out, cudaStream_t stream);
 // compact residency of the octree (internal nodes only, level order); *out is cudaMalloc'ed
 cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, uint64_t* n_internal_out,
                                 cudaStream_t stream);
@@ -28,9 +31,10 @@ cudaError_t launch_synth(uint32_t* grid, const SynthSpec& spec, cudaStream_t str
 cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride, unsigned long long* out,
                                cudaStream_t stream);
 // DDA skip table over 2^shift-voxel bricks with radii up to `cap` (layout: xn_device.cuh SkipTable);
-// *table_out is cudaMalloc'ed, dims_out = table extent in bricks including the one-brick border
+// *table_out is cudaMalloc'ed, dims_out = table extent in bricks including the one-brick border,
+// *uniform_fraction_out (nullable) = share of the grid's bricks that hold one colour
 cudaError_t build_skip_table(const uint32_t* grid, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift, uint32_t cap,
-                             uint4** table_out, uint32_t dims_out[3], cudaStream_t stream);
+                             uint4** table_out, uint32_t dims_out[3], double* uniform_fraction_out, cudaStream_t stream);
 cudaError_t launch_stats_totals(const uint32_t* steps, const unsigned long long* bytes, uint64_t n,
                                 unsigned long long* totals, cudaStream_t stream);
 } // namespace xn

@@ -12,37 +12,78 @@ namespace xn {
 // ---------------------------------------------------------------------------------
 // volume re-layout: 40-byte file nodes -> 64-byte device nodes (one thread per node)
 // ---------------------------------------------------------------------------------
-__global__ void relayout_nodes_kernel(const uint32_t* __restrict__ raw, uint64_t count, DNode* __restrict__ out,
-                                      uint32_t* __restrict__ max_depth) {
+__global__ void relayout_nodes_kernel(const uint32_t* __restrict__ raw, uint64_t count, DNode* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t my_depth = 0;
-    if (i < count) {
-        const uint32_t* n = raw + i * 10u;
-        my_depth = n[9] & 0x7FFFFFFFu;
-        DNode d;
+    if (i >= count) return;
+    const uint32_t* n = raw + i * 10u;
+    DNode d;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t child = n[c];
-            if (child >= count) child = 0; // malformed file: never index out of bounds
-            const uint32_t* cn = raw + (uint64_t)child * 10u;
-            d.slot[c] = make_uint2(child, make_meta(cn[8], cn[9]));
-        }
-        uint4* o = reinterpret_cast<uint4*>(out + i);
-        o[0] = make_uint4(d.slot[0].x, d.slot[0].y, d.slot[1].x, d.slot[1].y);
-        o[1] = make_uint4(d.slot[2].x, d.slot[2].y, d.slot[3].x, d.slot[3].y);
-        o[2] = make_uint4(d.slot[4].x, d.slot[4].y, d.slot[5].x, d.slot[5].y);
-        o[3] = make_uint4(d.slot[6].x, d.slot[6].y, d.slot[7].x, d.slot[7].y);
+    for (int c = 0; c < 8; ++c) {
+        uint32_t child = n[c];
+        if (child >= count) child = 0; // malformed file: never index out of bounds
+        const uint32_t* cn = raw + (uint64_t)child * 10u;
+        d.slot[c] = make_uint2(child, make_meta(cn[8], cn[9]));
     }
-    // block-wide max of depth -> one atomic per warp
+    uint4* o = reinterpret_cast<uint4*>(out + i);
+    o[0] = make_uint4(d.slot[0].x, d.slot[0].y, d.slot[1].x, d.slot[1].y);
+    o[1] = make_uint4(d.slot[2].x, d.slot[2].y, d.slot[3].x, d.slot[3].y);
+    o[2] = make_uint4(d.slot[4].x, d.slot[4].y, d.slot[5].x, d.slot[5].y);
+    o[3] = make_uint4(d.slot[6].x, d.slot[6].y, d.slot[7].x, d.slot[7].y);
+}
+
+// deepest node of the file (stack sizing, residency limits)
+__global__ void max_depth_kernel(const uint32_t* __restrict__ raw, uint64_t count, uint32_t* __restrict__ max_depth) {
+    uint32_t my_depth = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        my_depth = max(my_depth, raw[i * 10u + 9u] & 0x7FFFFFFFu);
     for (int o = 16; o > 0; o >>= 1) my_depth = max(my_depth, __shfl_xor_sync(0xFFFFFFFFu, my_depth, o));
     if ((threadIdx.x & 31) == 0 && my_depth) atomicMax(max_depth, my_depth);
 }
 
-cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, uint32_t* d_max_depth,
-                            cudaStream_t stream) {
+cudaError_t launch_max_depth(const void* raw40, uint64_t count, uint32_t* d_max_depth, cudaStream_t stream) {
+    max_depth_kernel<<<148 * 8, 256, 0, stream>>>((const uint32_t*)raw40, count, d_max_depth);
+    return cudaGetLastError();
+}
+
+// 40-byte file nodes -> 32-byte rope records (RNode, xn_device.cuh); one thread per node
+__global__ void relayout_rnodes_kernel(const uint32_t* __restrict__ raw, uint64_t count, RNode* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t* n = raw + i * 10u;
+    uint32_t w[8];
+    if (n[9] & 0x80000000u) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            uint32_t t = n[k];
+            if (t >= count) t = 0; // malformed file: never index out of bounds
+            w[k] = t == 0u ? 0u : (t | ((raw[(uint64_t)t * 10u + 9u] & 0xFu) << 28));
+        }
+        w[6] = (n[8] & 0x00FFFFFFu) | ((n[9] & 0xFFu) << 24);
+        w[7] = RNODE_LEAF_TAG;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t child = n[c];
+            if (child >= count) child = 0;
+            w[c] = child | (raw[(uint64_t)child * 10u + 9u] & 0x80000000u);
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+cudaError_t launch_relayout_rnodes(const void* raw40, uint64_t count, RNode* out, cudaStream_t stream) {
     const int threads = 256;
     const uint64_t blocks = (count + threads - 1) / threads;
-    relayout_nodes_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, out, d_max_depth);
+    relayout_rnodes_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, cudaStream_t stream) {
+    const int threads = 256;
+    const uint64_t blocks = (count + threads - 1) / threads;
+    relayout_nodes_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, out);
     return cudaGetLastError();
 }
 
@@ -375,8 +416,16 @@ __global__ void skip_relax_kernel(const uint4* __restrict__ in, uint4* __restric
     }
 }
 
+__global__ void skip_count_kernel(const uint4* __restrict__ table, uint64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long uniform = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        uniform += (table[i].x & SKIP_UNIFORM) != 0u;
+    for (int o = 16; o > 0; o >>= 1) uniform += __shfl_xor_sync(0xFFFFFFFFu, uniform, o);
+    if ((threadIdx.x & 31) == 0 && uniform) atomicAdd(out, uniform);
+}
+
 cudaError_t build_skip_table(const uint32_t* grid, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift, uint32_t cap,
-                             uint4** table_out, uint32_t dims_out[3], cudaStream_t stream) {
+                             uint4** table_out, uint32_t dims_out[3], double* uniform_fraction_out, cudaStream_t stream) {
     *table_out = nullptr;
     if (shift < 1u || shift > 5u || cap < 1u || cap > 255u) return cudaErrorInvalidValue;
     // the march's promise covers at most (cap - 1) B + B - 1 steps per axis; the rounding bound of
@@ -402,7 +451,17 @@ cudaError_t build_skip_table(const uint32_t* grid, uint32_t nx, uint32_t ny, uin
             b = t;
         }
         e = cudaGetLastError();
+        // share of the grid's own bricks (border layer excluded) that hold one colour
+        unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(b);
+        unsigned long long cnt = 0;
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, 8, stream);
+        if (e == cudaSuccess) {
+            skip_count_kernel<<<148 * 8, 256, 0, stream>>>(a, n, d_cnt);
+            e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, stream);
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        const uint64_t own = (uint64_t)bx * by * bz;
+        if (uniform_fraction_out) *uniform_fraction_out = (double)(cnt - (n - own)) / (double)own;
     }
     cudaFree(b);
     if (e != cudaSuccess) {

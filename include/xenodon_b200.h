@@ -112,10 +112,10 @@ XN_API int xn_upload_grid_tiff(xn_ctx* ctx, const char* path, uint64_t dims_out[
 /* same, from memory already resident on ctx's device (copied device-to-device) */
 XN_API int xn_upload_grid_device(xn_ctx* ctx, const void* d_rgba, uint64_t nx, uint64_t ny, uint64_t nz);
 XN_API int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uint64_t side);
-/* `xenodon convert --chan-diff n [--rope]` on the GPU, from the grid resident on ctx
- * (build_octree, src/model/OctreeConstruction.h:226-237; Octree::generate_ropes,
+/* `xenodon convert --chan-diff n [--dag | --rope]` on the GPU, from the grid resident on ctx
+ * (build_octree, src/model/OctreeConstruction.h:226-237; HashCache, :19-30; Octree::generate_ropes,
  * src/model/Octree.cpp:181-201).  The node array is byte-identical to the host builder's
- * (xn_build_octree) and so to the reference's.  type: 0 sparse, 2 rope (--dag and --std-dev are
+ * (xn_build_octree) and so to the reference's.  type: 0 sparse, 1 dag, 2 rope (--std-dev is
  * host-only).  nodes_out (nullable) receives a host copy (release with xn_free); bind != 0 also
  * makes the tree the context's resident octree, without a host round trip. */
 XN_API int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_node** nodes_out,

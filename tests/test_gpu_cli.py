@@ -58,7 +58,9 @@ def test_render_headless_tiff_and_svo(xb, xo, tmp_path):
         host = tmp_path / "host.svo"
         assert "Built on the host" in run(xb, "convert", "--host", *flags, tif, host)
         assert host.read_bytes() == path.read_bytes()
-    assert "Built on the host" in run(xb, "convert", "--dag", tif, tmp_path / "dag.svo")
+    assert "Built on the GPU" in run(xb, "convert", "--dag", tif, tmp_path / "dag.svo")
+    assert "Built on the host" in run(xb, "convert", "--host", "--dag", tif, tmp_path / "dag_host.svo")
+    assert (tmp_path / "dag.svo").read_bytes() == (tmp_path / "dag_host.svo").read_bytes()
     for shader, path in (("svo-naive", svo), ("svo-df", svo), ("esvo", svo), ("svo-rope", rope)):
         out = run(xb, "render", "--headless", conf, path, "-s", shader, "--camera", cam, "--repeat", "2",
                   "--discard-output", "--stats-output", stats, "-e", "4")

@@ -26,7 +26,7 @@ NVCC_HOST_FLAGS = ["-O2", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisi
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-pthread"]
 
 CU_SOURCES = [("xn_kernels.cu", NVCC_KERNEL_FLAGS), ("xn_util_kernels.cu", NVCC_HOST_FLAGS),
-              ("xn_convert.cu", NVCC_HOST_FLAGS),
+              ("xn_convert.cu", NVCC_HOST_FLAGS), ("xn_dag.cu", NVCC_HOST_FLAGS),
               ("xn_capi.cu", NVCC_HOST_FLAGS)]
 CPP_SOURCES = ["host/xn_tiff.cpp", "host/xn_svo.cpp", "host/xn_text.cpp", "host/xn_png.cpp", "host/xn_synth_host.cpp"]
 CLI_SOURCES = ["host/xn_cli.cpp"]

@@ -719,13 +719,13 @@ void convert(const std::vector<const char*>& args) {
     uint64_t count = 0, side = 0;
     xn_build_stats st{};
     const int type = dag ? 1 : rope ? 2 : 0;
-    // The GPU builder (byte-identical output) handles --chan-diff for sparse and rope trees; --dag,
+    // The GPU builder (byte-identical output) handles --chan-diff for sparse, dag and rope trees;
     // --std-dev, --host, or the absence of a CUDA device use the host builder.  On the GPU path the
     // volume goes from the file to the device through the ingest pipeline and never exists on the host.
     int rc = XN_ERR_INVALID;
     bool on_gpu = false;
     int n_devices = 0;
-    if (!host_only && stddev < 0 && !dag && xn_device_count(&n_devices) == XN_OK && n_devices > 0) {
+    if (!host_only && stddev < 0 && xn_device_count(&n_devices) == XN_OK && n_devices > 0) {
         xn_ctx* ctx = nullptr;
         if (xn_ctx_create(0, &ctx) == XN_OK) {
             xn_set_grid_layout(ctx, XN_GRID_LAYOUT_LINEAR); // the builder reads the x-major copy

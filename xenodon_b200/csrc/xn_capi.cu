@@ -780,15 +780,30 @@ int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_
         check_ctx(ctx);
         if (!ctx->have_grid()) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
         if (chan_diff < 0 || chan_diff > 255) throw xn::Error(XN_ERR_INVALID, "channel difference must be 0..255");
-        if (type != 0 && type != 2)
-            throw xn::Error(XN_ERR_INVALID, "the GPU builder makes sparse (0) and rope (2) trees; --dag is host-only");
+        if (type < 0 || type > 2) throw xn::Error(XN_ERR_INVALID, "unknown octree type");
         if (nodes_out) *nodes_out = nullptr;
         DeviceGuard g(ctx->device);
         ensure_linear(ctx); // the builder reads the x-major copy
         void* d_nodes = nullptr;
         uint64_t count = 0, side = 0;
+        xn_build_stats stats{};
         xn::gpu_build_octree(ctx->grid, ctx->nx, ctx->ny, ctx->nz, (uint32_t)chan_diff, type == 2, ctx->stream, &d_nodes,
-                             &count, &side, stats_out);
+                             &count, &side, &stats);
+        if (type == 1) { // --dag: one representative per class of identical subtrees
+            void* d_dag = nullptr;
+            uint64_t dag_count = 0, unique_leaves = 0;
+            try {
+                xn::gpu_dag_from_sparse(d_nodes, count, ctx->stream, &d_dag, &dag_count, &unique_leaves);
+            } catch (...) {
+                cudaFree(d_nodes);
+                throw;
+            }
+            cudaFree(d_nodes);
+            d_nodes = d_dag;
+            count = dag_count;
+            stats.unique_leaves = unique_leaves; // total_nodes / total_leaves keep counting every visit, as the reference does
+        }
+        if (stats_out) *stats_out = stats;
         try {
             if (nodes_out) {
                 xn_node* host = (xn_node*)std::malloc(std::max<uint64_t>(count, 1) * sizeof(xn_node));

@@ -12,4 +12,9 @@ namespace xn {
 void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t chan_diff, bool rope,
                       cudaStream_t stream, void** d_nodes_out, uint64_t* count_out, uint64_t* side_out,
                       xn_build_stats* stats_out);
+// `--dag`: merges identical subtrees of a sparse (non-rope) tree built by gpu_build_octree, byte-identical
+// to the reference's HashCache builder (src/model/OctreeConstruction.h:19-30).  d_sparse stays owned
+// by the caller; *d_dag_out is cudaMalloc'ed.
+void gpu_dag_from_sparse(const void* d_sparse, uint64_t count, cudaStream_t stream, void** d_dag_out, uint64_t* dag_count_out,
+                         uint64_t* unique_leaves_out);
 } // namespace xn

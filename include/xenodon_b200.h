@@ -115,11 +115,19 @@ XN_API int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t cou
 /* `xenodon convert --chan-diff n [--dag | --rope]` on the GPU, from the grid resident on ctx
  * (build_octree, src/model/OctreeConstruction.h:226-237; HashCache, :19-30; Octree::generate_ropes,
  * src/model/Octree.cpp:181-201).  The node array is byte-identical to the host builder's
- * (xn_build_octree) and so to the reference's.  type: 0 sparse, 1 dag, 2 rope (--std-dev is
- * host-only).  nodes_out (nullable) receives a host copy (release with xn_free); bind != 0 also
+ * (xn_build_octree) and so to the reference's.  type: 0 sparse, 1 dag, 2 rope.  nodes_out (nullable) receives a host copy (release with xn_free); bind != 0 also
  * makes the tree the context's resident octree, without a host round trip. */
 XN_API int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_node** nodes_out,
                                     uint64_t* count_out, uint64_t* side_out, xn_build_stats* stats_out);
+/* The same with either split heuristic (ChannelDiffHeuristic / StdDevHeuristic,
+ * src/model/OctreeConstruction.h:32-48): heuristic 0 = --chan-diff (param 0..255), 1 = --std-dev
+ * (param >= 0).  --std-dev is decided from exact integer sums with a bound on the rounding of the
+ * reference's binary64 evaluation (src/model/Grid.cpp:139-214); when the threshold lies within that
+ * bound of some cell's deviation the call fails with XN_ERR_LIMIT instead of guessing, and
+ * xn_build_octree (host, replays the reference's additions) decides. */
+XN_API int xn_convert_resident_grid_ex(xn_ctx* ctx, int heuristic, double param, int type, int bind,
+                                       xn_node** nodes_out, uint64_t* count_out, uint64_t* side_out,
+                                       xn_build_stats* stats_out);
 /* deterministic synthetic volumes generated directly in device memory
  * (BASELINE.md section 4): kind 0 = "bunny-CT", 1 = "TNG gas"; bound as the grid */
 XN_API int xn_synth_grid_device(xn_ctx* ctx, int kind, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t seed);

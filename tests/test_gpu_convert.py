@@ -100,6 +100,41 @@ def test_gpu_dag_matches_reference_digests_and_renders(xb, xo):
         ctx.close()
 
 
+def test_gpu_std_dev_matches_reference_digests_and_oracle(xb, xo):
+    """`convert --std-dev` on the GPU decides every split from exact integer sums plus a rigorous
+    bound on the rounding of the reference's binary64 evaluation: the .svo bytes equal the
+    reference's digests (sd0, sd40 fixtures, all three tree types) and the oracle's on random /
+    smooth volumes for a sweep of thresholds; a threshold that coincides with a cell's deviation
+    (0.5 on a cell of four 0s and four 1s) is refused with XN_ERR_LIMIT, never guessed."""
+    import hashlib
+    import os
+    import struct
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "convert_golden.npz"))
+    for gname in ("rand_20x9x5", "blob_24", "noise_8"):
+        g = z[f"{gname}/grid"]
+        for ttype in (0, 1, 2):
+            for hname, sd in (("sd0", 0.0), ("sd40", 40.0)):
+                tree, st, count, side = _gpu_convert(xb, g, std_dev=sd, type=ttype)
+                raw = b"XNDN-SVO" + struct.pack("<QQ", side, count) + tree.nodes.tobytes()
+                assert hashlib.sha256(raw).digest() == z[f"{gname}/t{ttype}_{hname}/sha256"].tobytes(), (gname, ttype, hname)
+    rng = np.random.default_rng(99)
+    for g in (random_grid(rng, 33, 20, 17, quant=16), blobby_grid(rng, 40, 29, 33),
+              rng.integers(0, 256, (16, 16, 16, 4), dtype=np.uint8)):
+        for sd in (0.0, 0.3, 7.77, 31.0, 90.0, 300.0):
+            tree, st, count, side = _gpu_convert(xb, g, std_dev=sd, type=xb.TYPE_SPARSE)
+            onodes, oside, ost = xo.build_octree(g, std_dev=sd, type=xo.TYPE_SPARSE)
+            assert tree.nodes.tobytes() == onodes.tobytes() and st == ost, sd
+    g = np.zeros((2, 2, 2, 4), np.uint8)
+    g[0, :, :, 0] = 1  # channel r: four 0s, four 1s -> deviation exactly 0.5
+    with pytest.raises(xb.XenodonError) as e:
+        _gpu_convert(xb, g, std_dev=0.5)
+    assert e.value.status == -5 and "host builder" in str(e.value)
+    tree, _, count, _ = _gpu_convert(xb, g, std_dev=0.4999)
+    assert count == 9
+    tree, _, count, _ = _gpu_convert(xb, g, std_dev=0.5001)
+    assert count == 1
+
+
 def test_gpu_convert_rejects_bad_arguments(xb):
     ctx = xb.Context(0)
     ctx.upload_grid(xb.Grid(np.zeros((4, 4, 4, 4), np.uint8)))

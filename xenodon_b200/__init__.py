@@ -84,6 +84,8 @@ _PROTOTYPES = {
     "xn_upload_svo_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "xn_convert_resident_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(BuildStats)]),
+    "xn_convert_resident_grid_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(BuildStats)]),
     "xn_synth_grid_device": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]),
     "xn_synth_grid_host": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "xn_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -372,12 +374,15 @@ class Context:
         return Grid(out)
 
     def convert_resident_grid(self, chan_diff: int = 0, type: int = TYPE_SPARSE, bind: bool = True,
-                              want_nodes: bool = False):
-        """GPU `xenodon convert` of the resident grid -> (Octree | None, stats dict, count, side)."""
+                              want_nodes: bool = False, std_dev=None):
+        """GPU `xenodon convert` of the resident grid -> (Octree | None, stats dict, count, side).
+        std_dev selects the --std-dev heuristic (XenodonError with status -5 when the threshold is
+        within rounding distance of a cell's deviation: build_octree on the host decides those)."""
         out, count, side, st = C.c_void_p(), C.c_uint64(), C.c_uint64(), BuildStats()
-        _check(lib().xn_convert_resident_grid(self._h, chan_diff, type, int(bind),
-                                              C.byref(out) if want_nodes else None, C.byref(count), C.byref(side),
-                                              C.byref(st)))
+        heur, param = (HEUR_STD_DEV, float(std_dev)) if std_dev is not None else (HEUR_CHAN_DIFF, float(chan_diff))
+        _check(lib().xn_convert_resident_grid_ex(self._h, heur, param, type, int(bind),
+                                                 C.byref(out) if want_nodes else None, C.byref(count), C.byref(side),
+                                                 C.byref(st)))
         tree = None
         if want_nodes:
             try:

@@ -719,18 +719,20 @@ void convert(const std::vector<const char*>& args) {
     uint64_t count = 0, side = 0;
     xn_build_stats st{};
     const int type = dag ? 1 : rope ? 2 : 0;
-    // The GPU builder (byte-identical output) handles --chan-diff for sparse, dag and rope trees;
-    // --std-dev, --host, or the absence of a CUDA device use the host builder.  On the GPU path the
+    // The GPU builder (byte-identical output) handles both heuristics and all three tree types; --host,
+    // the absence of a CUDA device, or a --std-dev threshold within rounding distance of some cell's
+    // deviation (the GPU builder refuses to guess) use the host builder.  On the GPU path the
     // volume goes from the file to the device through the ingest pipeline and never exists on the host.
     int rc = XN_ERR_INVALID;
     bool on_gpu = false;
     int n_devices = 0;
-    if (!host_only && stddev < 0 && xn_device_count(&n_devices) == XN_OK && n_devices > 0) {
+    if (!host_only && xn_device_count(&n_devices) == XN_OK && n_devices > 0) {
         xn_ctx* ctx = nullptr;
         if (xn_ctx_create(0, &ctx) == XN_OK) {
             xn_set_grid_layout(ctx, XN_GRID_LAYOUT_LINEAR); // the builder reads the x-major copy
             if (xn_upload_grid_tiff(ctx, src.c_str(), nullptr, nullptr) == XN_OK)
-                rc = xn_convert_resident_grid(ctx, std::max(channel_difference, 0), type, 0, &nodes, &count, &side, &st);
+                rc = stddev >= 0 ? xn_convert_resident_grid_ex(ctx, 1, stddev, type, 0, &nodes, &count, &side, &st)
+                                 : xn_convert_resident_grid(ctx, std::max(channel_difference, 0), type, 0, &nodes, &count, &side, &st);
             xn_ctx_destroy(ctx);
             on_gpu = rc == XN_OK;
         }

@@ -776,10 +776,18 @@ int xn_upload_svo_device(xn_ctx* ctx, const void* d_nodes40, uint64_t count, uin
 
 int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_node** nodes_out, uint64_t* count_out,
                              uint64_t* side_out, xn_build_stats* stats_out) {
+    if (chan_diff < 0 || chan_diff > 255) return fail(XN_ERR_INVALID, "channel difference must be 0..255");
+    return xn_convert_resident_grid_ex(ctx, 0, (double)chan_diff, type, bind, nodes_out, count_out, side_out, stats_out);
+}
+
+int xn_convert_resident_grid_ex(xn_ctx* ctx, int heuristic, double param, int type, int bind, xn_node** nodes_out,
+                                uint64_t* count_out, uint64_t* side_out, xn_build_stats* stats_out) {
     return guarded([&] {
         check_ctx(ctx);
         if (!ctx->have_grid()) throw xn::Error(XN_ERR_INVALID, "no grid is resident");
-        if (chan_diff < 0 || chan_diff > 255) throw xn::Error(XN_ERR_INVALID, "channel difference must be 0..255");
+        if (heuristic != 0 && heuristic != 1) throw xn::Error(XN_ERR_INVALID, "unknown split heuristic");
+        if (heuristic == 0 && !(param >= 0.0 && param <= 255.0)) throw xn::Error(XN_ERR_INVALID, "channel difference must be 0..255");
+        if (heuristic == 1 && !(param >= 0.0)) throw xn::Error(XN_ERR_INVALID, "standard deviation must be >= 0");
         if (type < 0 || type > 2) throw xn::Error(XN_ERR_INVALID, "unknown octree type");
         if (nodes_out) *nodes_out = nullptr;
         DeviceGuard g(ctx->device);
@@ -787,7 +795,7 @@ int xn_convert_resident_grid(xn_ctx* ctx, int chan_diff, int type, int bind, xn_
         void* d_nodes = nullptr;
         uint64_t count = 0, side = 0;
         xn_build_stats stats{};
-        xn::gpu_build_octree(ctx->grid, ctx->nx, ctx->ny, ctx->nz, (uint32_t)chan_diff, type == 2, ctx->stream, &d_nodes,
+        xn::gpu_build_octree(ctx->grid, ctx->nx, ctx->ny, ctx->nz, heuristic, param, type == 2, ctx->stream, &d_nodes,
                              &count, &side, &stats);
         if (type == 1) { // --dag: one representative per class of identical subtrees
             void* d_dag = nullptr;

@@ -13,8 +13,9 @@
 //          index(child k) = index(parent) + 1 + sum_{j > k} size(child j),
 //      and writes the 40-byte node records (children mirrored into the reversed numbering);
 //   3. (--rope) one pass over the leaves runs the six Octree::find descents per leaf.
-// All arithmetic is integer; every voxel is read once.  DAG merging (--dag) and the --std-dev
-// heuristic (order-dependent binary64 sums) stay on the host builder.
+// All arithmetic is integer; every voxel is read once.  --std-dev is decided from exact integer
+// sums with a rigorous bound on the reference's binary64 rounding (SplitRule below); DAG merging
+// (--dag) is a pass over the finished sparse array (xn_dag.cu).
 #include <algorithm>
 #include <vector>
 
@@ -62,16 +63,54 @@ struct Level {
     SumT* sum; // 4 per cell
     uint32_t* si;
     uint32_t cells; // per axis
+    unsigned long long* sq; // --std-dev only: sum over the cell's voxels and channels of x^2 (else nullptr)
 };
 
+// Split rule of the two heuristics (src/model/OctreeConstruction.h:32-48).
+//   --chan-diff: vol_scan's max channel difference > threshold (integers).
+//   --std-dev  : stddev_scan's sqrt(sum((x - avg)^2) / n) > threshold, which the reference evaluates
+//     in binary64 with one rounded addition per voxel (src/model/Grid.cpp:139-214).  The exact
+//     value follows from integer sums, V = (n Q - sum_c A_c^2) / n^2 with A_c = sum x_c and
+//     Q = sum x^2; the reference's rounded result differs from sqrt(V) by a relative error of at
+//     most tau = (n + 16) 2^-54 (n - 1 additions of non-negative terms, a handful of roundings per
+//     term, one division, one square root).  The verdict is therefore CERTAIN unless V lies within
+//     a factor 1 +- 8 tau of threshold^2; such a cell is counted in *uncertain and the caller gives
+//     the volume to the host builder, which replays the reference's additions.  threshold = 0 is
+//     exact: the deviation is 0 iff every voxel equals the average.
+struct SplitRule {
+    int heuristic;      // 0 --chan-diff, 1 --std-dev
+    uint32_t chan_diff;
+    double std_dev;
+};
+template <typename SumT>
+__device__ __forceinline__ bool wants_split(const SplitRule& rule, uint32_t mn, uint32_t mx, const SumT s[4],
+                                            unsigned long long q, uint64_t n, unsigned long long* uncertain) {
+    if (rule.heuristic == 0) return max_diff(mn, mx) > rule.chan_diff;
+    if (n == 0) return false;
+    unsigned __int128 t = (unsigned __int128)n * q;
+    for (int c = 0; c < 4; ++c) t -= (unsigned __int128)(uint64_t)s[c] * (uint64_t)s[c]; // n Q >= sum A_c^2 (Cauchy-Schwarz)
+    if (rule.std_dev == 0.0) return t != 0;
+    const double td = (double)(uint64_t)(t >> 64) * 18446744073709551616.0 + (double)(uint64_t)t;
+    const double nd = (double)n;
+    const double v = td / (nd * nd);
+    const double thr2 = rule.std_dev * rule.std_dev;
+    const double tau = (nd + 16.0) * 5.551115123125783e-17; // 2^-54
+    if (v > thr2 * (1.0 + 8.0 * tau)) return true;
+    if (v < thr2 * (1.0 - 8.0 * tau)) return false;
+    atomicAdd(uncertain, 1ull);
+    return false;
+}
+
 // ---- bottom-up, level 1: children are voxels ----
-__global__ void pyramid_level1(const uint32_t* __restrict__ grid, Dims d, Level<uint32_t> out, uint32_t thr) {
+__global__ void pyramid_level1(const uint32_t* __restrict__ grid, Dims d, Level<uint32_t> out, SplitRule rule,
+                               unsigned long long* uncertain) {
     const uint64_t total = (uint64_t)out.cells * out.cells * out.cells;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t cx = (uint32_t)(c % out.cells), cy = (uint32_t)((c / out.cells) % out.cells),
                        cz = (uint32_t)(c / ((uint64_t)out.cells * out.cells));
         const uint32_t ox = cx * 2, oy = cy * 2, oz = cz * 2;
         uint32_t mn = 0xFFFFFFFFu, mx = 0u, s[4] = {0, 0, 0, 0};
+        unsigned long long q = 0;
         if (ox < d.nx && oy < d.ny && oz < d.nz) {
             for (uint32_t z = oz; z < min(oz + 2, d.nz); ++z)
                 for (uint32_t y = oy; y < min(oy + 2, d.ny); ++y)
@@ -83,9 +122,11 @@ __global__ void pyramid_level1(const uint32_t* __restrict__ grid, Dims d, Level<
                         s[1] += (v >> 8) & 0xFFu;
                         s[2] += (v >> 16) & 0xFFu;
                         s[3] += v >> 24;
+                        q += (v & 0xFFu) * (v & 0xFFu) + ((v >> 8) & 0xFFu) * ((v >> 8) & 0xFFu) +
+                             ((v >> 16) & 0xFFu) * ((v >> 16) & 0xFFu) + (v >> 24) * (v >> 24);
                     }
             const bool fully_in = ox + 2 <= d.nx && oy + 2 <= d.ny && oz + 2 <= d.nz;
-            const bool leaf = !(max_diff(mn, mx) > thr) && fully_in;
+            const bool leaf = !wants_split(rule, mn, mx, s, q, clipped_count(d, ox, oy, oz, 2), uncertain) && fully_in;
             out.si[c] = TOP | (leaf ? 1u : 9u);
         } else {
             out.si[c] = TOP | 1u; // outside the source grid: black leaf
@@ -96,13 +137,14 @@ __global__ void pyramid_level1(const uint32_t* __restrict__ grid, Dims d, Level<
         out.sum[4 * c + 1] = s[1];
         out.sum[4 * c + 2] = s[2];
         out.sum[4 * c + 3] = s[3];
+        if (out.sq) out.sq[c] = q;
     }
 }
 
 // ---- bottom-up, level L >= 2: children are cells of level L-1 ----
 template <typename ChildSumT, typename SumT>
-__global__ void pyramid_level(Level<ChildSumT> in, Level<SumT> out, Dims d, uint32_t extent, uint32_t thr,
-                              unsigned long long* overflow) {
+__global__ void pyramid_level(Level<ChildSumT> in, Level<SumT> out, Dims d, uint32_t extent, SplitRule rule,
+                              unsigned long long* overflow, unsigned long long* uncertain) {
     const uint64_t total = (uint64_t)out.cells * out.cells * out.cells;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t cx = (uint32_t)(c % out.cells), cy = (uint32_t)((c / out.cells) % out.cells),
@@ -110,6 +152,7 @@ __global__ void pyramid_level(Level<ChildSumT> in, Level<SumT> out, Dims d, uint
         const uint32_t ox = cx * extent, oy = cy * extent, oz = cz * extent;
         uint32_t mn = 0xFFFFFFFFu, mx = 0u;
         SumT s[4] = {0, 0, 0, 0};
+        unsigned long long q = 0;
         uint32_t word = TOP | 1u;
         if (ox < d.nx && oy < d.ny && oz < d.nz) {
             uint64_t size = 1;
@@ -120,9 +163,11 @@ __global__ void pyramid_level(Level<ChildSumT> in, Level<SumT> out, Dims d, uint
                 mn = min4(mn, in.mn[kc]); // cells outside the grid hold the neutral elements
                 mx = max4(mx, in.mx[kc]);
                 for (int ch = 0; ch < 4; ++ch) s[ch] += (SumT)in.sum[4 * kc + ch];
+                if (in.sq) q += in.sq[kc];
             }
             const bool fully_in = ox + extent <= d.nx && oy + extent <= d.ny && oz + extent <= d.nz;
-            const bool leaf = !(max_diff(mn, mx) > thr) && fully_in;
+            const bool leaf =
+                !wants_split(rule, mn, mx, s, q, clipped_count(d, ox, oy, oz, extent), uncertain) && fully_in;
             if (leaf) size = 1;
             if (size >= TOP) atomicAdd(overflow, 1ull); // more than 2^31 - 1 nodes: not representable here
             word = TOP | (uint32_t)size;
@@ -131,6 +176,7 @@ __global__ void pyramid_level(Level<ChildSumT> in, Level<SumT> out, Dims d, uint
         out.mn[c] = mn;
         out.mx[c] = mx;
         for (int ch = 0; ch < 4; ++ch) out.sum[4 * c + ch] = s[ch];
+        if (out.sq) out.sq[c] = q;
     }
 }
 
@@ -305,9 +351,14 @@ int blocks_for(uint64_t cells_total) {
 
 } // namespace
 
-void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t chan_diff, bool rope,
+void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t nz, int heuristic, double param, bool rope,
                       cudaStream_t stream, void** d_nodes_out, uint64_t* count_out, uint64_t* side_out,
                       xn_build_stats* stats_out) {
+    if (heuristic != 0 && heuristic != 1) throw Error(XN_ERR_INVALID, "gpu_build_octree: unknown heuristic");
+    if (heuristic == 0 && !(param >= 0.0 && param <= 255.0)) throw Error(XN_ERR_INVALID, "channel difference must be 0..255");
+    if (heuristic == 1 && !(param >= 0.0)) throw Error(XN_ERR_INVALID, "standard deviation must be >= 0");
+    const SplitRule rule{heuristic, heuristic == 0 ? (uint32_t)param : 0u, heuristic == 1 ? param : 0.0};
+    const bool want_sq = heuristic == 1;
     if (!d_grid || nx == 0 || ny == 0 || nz == 0) throw Error(XN_ERR_INVALID, "gpu_build_octree: empty grid");
     const uint64_t dim = std::max({ceil_2pow(nx), ceil_2pow(ny), ceil_2pow(nz)});
     if (dim > 65536) throw Error(XN_ERR_LIMIT, "gpu_build_octree: grid too large");
@@ -342,43 +393,48 @@ void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t
     for (int L = 1; L <= lmax; ++L) {
         const uint32_t cells = (uint32_t)(dim >> L);
         const uint64_t total = (uint64_t)cells * cells * cells;
+        unsigned long long* sq = want_sq ? buf.alloc<unsigned long long>(total) : nullptr;
         if (L < WIDE_FROM)
             lo[L] = Level<uint32_t>{buf.alloc<uint32_t>(total), buf.alloc<uint32_t>(total), buf.alloc<uint32_t>(4 * total),
-                                    buf.alloc<uint32_t>(total), cells};
+                                    buf.alloc<uint32_t>(total), cells, sq};
         else
             hi[L] = Level<uint64_t>{buf.alloc<uint32_t>(total), buf.alloc<uint32_t>(total), buf.alloc<uint64_t>(4 * total),
-                                    buf.alloc<uint32_t>(total), cells};
+                                    buf.alloc<uint32_t>(total), cells, sq};
     }
-    unsigned long long* d_overflow = buf.alloc<unsigned long long>(1);
+    unsigned long long* d_overflow = buf.alloc<unsigned long long>(2); // [0] node-count overflow, [1] uncertain verdicts
+    unsigned long long* d_uncertain = d_overflow + 1;
     uint32_t* d_used = buf.alloc<uint32_t>(lmax + 2);
-    check(cudaMemsetAsync(d_overflow, 0, 8, stream), "cudaMemsetAsync");
+    check(cudaMemsetAsync(d_overflow, 0, 16, stream), "cudaMemsetAsync");
     check(cudaMemsetAsync(d_used, 0, (lmax + 2) * 4, stream), "cudaMemsetAsync");
 
     // 1. bottom-up
-    pyramid_level1<<<blocks_for((uint64_t)lo[1].cells * lo[1].cells * lo[1].cells), 256, 0, stream>>>(d_grid, d, lo[1],
-                                                                                                 chan_diff);
+    pyramid_level1<<<blocks_for((uint64_t)lo[1].cells * lo[1].cells * lo[1].cells), 256, 0, stream>>>(d_grid, d, lo[1], rule,
+                                                                                                 d_uncertain);
     for (int L = 2; L <= lmax; ++L) {
         const uint32_t extent = 1u << L;
         const uint32_t cells = (uint32_t)(dim >> L);
         const int blocks = blocks_for((uint64_t)cells * cells * cells);
         if (L < WIDE_FROM)
-            pyramid_level<uint32_t, uint32_t><<<blocks, 256, 0, stream>>>(lo[L - 1], lo[L], d, extent, chan_diff, d_overflow);
+            pyramid_level<uint32_t, uint32_t><<<blocks, 256, 0, stream>>>(lo[L - 1], lo[L], d, extent, rule, d_overflow, d_uncertain);
         else if (L == WIDE_FROM)
-            pyramid_level<uint32_t, uint64_t><<<blocks, 256, 0, stream>>>(lo[L - 1], hi[L], d, extent, chan_diff, d_overflow);
+            pyramid_level<uint32_t, uint64_t><<<blocks, 256, 0, stream>>>(lo[L - 1], hi[L], d, extent, rule, d_overflow, d_uncertain);
         else
-            pyramid_level<uint64_t, uint64_t><<<blocks, 256, 0, stream>>>(hi[L - 1], hi[L], d, extent, chan_diff, d_overflow);
+            pyramid_level<uint64_t, uint64_t><<<blocks, 256, 0, stream>>>(hi[L - 1], hi[L], d, extent, rule, d_overflow, d_uncertain);
     }
     check(cudaGetLastError(), "pyramid kernels");
 
     // root verdict
     uint32_t root_word = 0, root_mn = 0;
-    unsigned long long overflow = 0;
+    unsigned long long overflow[2] = {0, 0};
     uint32_t* root_si = lmax < WIDE_FROM ? lo[lmax].si : hi[lmax].si;
     check(cudaMemcpyAsync(&root_word, root_si, 4, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync");
-    check(cudaMemcpyAsync(&overflow, d_overflow, 8, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync");
+    check(cudaMemcpyAsync(overflow, d_overflow, 16, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync");
     check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
     (void)root_mn;
-    if (overflow) throw Error(XN_ERR_LIMIT, "octree exceeds 2^31 - 1 nodes (GPU builder limit)");
+    if (overflow[1])
+        throw Error(XN_ERR_LIMIT, "--std-dev: the threshold lies within rounding distance of " + std::to_string(overflow[1]) +
+                                      " cell deviation(s); only the host builder replays the reference's additions");
+    if (overflow[0]) throw Error(XN_ERR_LIMIT, "octree exceeds 2^31 - 1 nodes (GPU builder limit)");
     const uint64_t count = root_word & ~TOP;
 
     uint32_t* d_nodes = nullptr;

@@ -9,7 +9,9 @@
 namespace xn {
 // Builds the octree of an RGBA8 grid resident on the current device.  *d_nodes_out receives a
 // cudaMalloc'ed array of *count_out 40-byte nodes (the .svo node array, node 0 = root).
-void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t nz, uint32_t chan_diff, bool rope,
+// heuristic 0 = --chan-diff (param 0..255), 1 = --std-dev (param >= 0; XN_ERR_LIMIT when the threshold
+// is within rounding distance of a cell's deviation: the host builder decides those).
+void gpu_build_octree(const uint32_t* d_grid, uint64_t nx, uint64_t ny, uint64_t nz, int heuristic, double param, bool rope,
                       cudaStream_t stream, void** d_nodes_out, uint64_t* count_out, uint64_t* side_out,
                       xn_build_stats* stats_out);
 // `--dag`: merges identical subtrees of a sparse (non-rope) tree built by gpu_build_octree, byte-identical

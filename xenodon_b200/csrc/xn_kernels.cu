@@ -731,8 +731,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_TEX_MIN_BLOCKS) dda_tex_kern
 #ifndef XN_SKIP_MIN_BLOCKS
 #define XN_SKIP_MIN_BLOCKS 4
 #endif
+// known stretches: 0 = full trips only, 1 = counted bare trips (geometry only, warp-wide count),
+// 2 = per-lane closed-form jump over all steps that end before the promise does (dda_axis_jump)
 #ifndef XN_SKIP_BARE
-#define XN_SKIP_BARE 1
+#define XN_SKIP_BARE 2
+#endif
+// jump when a lane of the warp has at least this many steps of known texels ahead
+#ifndef XN_SKIP_JUMP_MIN
+#define XN_SKIP_JUMP_MIN 24
 #endif
 // look the table up this many trips before the promise runs out
 #ifndef XN_SKIP_EARLY
@@ -760,6 +766,46 @@ struct TexUniform<true> {
                            (unsigned char)((rgb >> 16) & 0xFFu), 0);
     }
 };
+
+// Closed form of the march's repeated additions (XN_SKIP_BARE == 2).  A side distance advances by
+//     s <- fl(s + d)       (binary32, round to nearest even, d > 0)
+// once per crossing of its axis, whatever the other axes do.  While s stays inside one binade
+// [2^e, 2^(e+1)) every sum is rounded to a multiple of the SAME u = 2^(e-23), and s itself is such a
+// multiple, so fl(s + d) = s + q with q = d rounded to a multiple of u: the crossings of an axis are
+// an exact arithmetic progression inside a binade, s_j = s + j q, with q read off one real addition
+// (q = fl(s + d) - s, exact).  [If d ends exactly on u / 2 the rounding is a tie, resolved towards
+// the even multiple: the result of any such addition is even, and from an even s the increment is
+// again constant -- so the progression is used from an even s only.]  All crossings below a time T
+// are therefore taken in O(binades) operations instead of O(crossings), and land on bit-identical
+// values: j = the largest count with s + j q < min(T, 2^(e+1)) comes from an under-estimate of the
+// quotient plus exact single steps (every s + j q below 2^(e+1) is representable, so fma(j, q, s) and
+// the corrections are exact); the addition that leaves the binade, and the one after it, are real ones.
+// On return s is the first crossing not below T, kf has grown by the crossings taken and t_last is
+// the latest of them.  (Prototype checked against the sequential additions on 3 10^5 random
+// (s, d, T) including tie-prone d: tools/jump_proto.py.)
+__device__ __forceinline__ void dda_axis_jump(float& s, const float d, const float T, float& t_last, float& kf) {
+    while (s < T) {
+        t_last = fmaxf(t_last, s);
+        s += d;
+        kf += 1.0f;
+        if (!(s < T)) break;
+        const float q = (s + d) - s;
+        const uint32_t sb = __float_as_uint(s), eb = sb & 0x7F800000u;
+        const float top = __uint_as_float(eb + 0x00800000u);    // 2^(e+1)
+        const float half_u = __uint_as_float(eb - (24u << 23)); // 2^(e-24)
+        if (s + d < top && (fabsf(d - q) != half_u || (sb & 1u) == 0u)) {
+            const float hi = fminf(T, top);
+            float jf = floorf(__fdividef(hi - s, q) * 0.99999f);
+            float sj = __fmaf_rn(jf, q, s);
+            while (sj + q < hi) {
+                sj += q;
+                jf += 1.0f;
+            }
+            s = sj;
+            kf += jf;
+        }
+    }
+}
 
 template <bool STATS, bool STRICT>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
@@ -809,6 +855,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         const float td_look = 8.0f * td_min;                    // spacing floor of table look-ups (two trips)
         const float inv_trip = 0.999999f / (4.00390625f * td_min); // trips per unit of t, rounded down a little
         const float itdx = 1.0f / tdx, itdy = 1.0f / tdy, itdz = 1.0f / tdz;
+        const float isum = (itdx + itdy) + itdz; // steps per unit of t
         // longest bare run, in trips minus one: an axis' side distance takes at most 4 n + 1 additions in
         // n trips, each rounded by at most 2^-24 (t_end + td_i), so the step count recovered from it is
         // off by less than (4 n + 1) 2^-24 (t_end / td_min + 1) -- kept below a quarter
@@ -905,7 +952,47 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
     {                                                                                               \
         const unsigned am = __activemask();                                                         \
         if (__any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                                      \
-        if (!STRICT && XN_SKIP_BARE) {                                                              \
+        if (!STRICT && XN_SKIP_BARE == 2) {                                                         \
+            /* every step that ends before T lands on a promised texel and leaves a whole trip before */ \
+            /* the end of the ray: take them all at once, each lane its own T                        */ \
+            const float T = fminf(t_safe - td45, t_lim4);                                           \
+            const bool can = pf == 0.0f && t < T;                                                   \
+            if (__any_sync(am, can && (T - t) * isum >= (float)XN_SKIP_JUMP_MIN)) {                   \
+                if (can) {                                                                          \
+                    float tl = t, kx = 0.0f, ky = 0.0f, kz = 0.0f;                                  \
+                    if (STATS) {                                                                    \
+                        /* the instrumented build takes the same steps one by one (counting them) */ \
+                        /* and checks the closed form against them: a mismatch poisons the count  */ \
+                        float cx = sdx, cy = sdy, cz = sdz;                                         \
+                        dda_axis_jump(cx, tdx, T, tl, kx);                                          \
+                        dda_axis_jump(cy, tdy, T, tl, ky);                                          \
+                        dda_axis_jump(cz, tdz, T, tl, kz);                                          \
+                        float qx = 0.0f, qy = 0.0f, qz = 0.0f, tq = t;                              \
+                        while (fminf(sdx, fminf(sdy, sdz)) < T) {                                   \
+                            const float t0 = fminf(sdx, fminf(sdy, sdz));                           \
+                            const bool mx = sdx == t0, my = sdy == t0, mz = sdz == t0;              \
+                            tq = t0;                                                                \
+                            if (mx) { sdx += tdx; qx += 1.0f; }                                     \
+                            if (my) { sdy += tdy; qy += 1.0f; }                                     \
+                            if (mz) { sdz += tdz; qz += 1.0f; }                                     \
+                            st.step();                                                              \
+                            st.read(XN_SKIP_DEBUG == 0 ? 4u : (XN_SKIP_DEBUG == 1 ? 1u : 0u));      \
+                        }                                                                           \
+                        if (cx != sdx || cy != sdy || cz != sdz || kx != qx || ky != qy || kz != qz || tl != tq) \
+                            st.steps |= 0x40000000u;                                                \
+                    } else {                                                                        \
+                        dda_axis_jump(sdx, tdx, T, tl, kx);                                         \
+                        dda_axis_jump(sdy, tdy, T, tl, ky);                                         \
+                        dda_axis_jump(sdz, tdz, T, tl, kz);                                         \
+                    }                                                                               \
+                    fx = __fmaf_rn(sg.x, kx, fx);                                                   \
+                    fy = __fmaf_rn(sg.y, ky, fy);                                                   \
+                    fz = __fmaf_rn(sg.z, kz, fz);                                                   \
+                    klen += tl - t;                                                                 \
+                    t = tl;                                                                         \
+                }                                                                                   \
+            }                                                                                       \
+        } else if (!STRICT && XN_SKIP_BARE == 1) {                                                  \
             /* trips certain to be known: the k-th starts before t + 4 k td_min (1 + 2^-10), and must  */ \
             /* start before min(t_safe, t_end) - 4.5 td_min; +1 because trip 0 starts at t itself; a */ \
             /* negative count converts to 0                                                          */ \

@@ -113,6 +113,7 @@ struct xn_ctx {
     uint4* skip_table = nullptr; // DDA skip table of the resident grid (any layout)
     uint32_t skip_dim[3] = {0, 0, 0}, skip_shift = 0;
     double skip_uniform = 0.0; // share of the grid's bricks that hold one colour
+    uint32_t* ray_pool = nullptr; // counter of the persistent ray pool (xn_kernels.cu, XN_RAY_POOL=1)
 
     // target
     xn_rect output{0, 0, 0, 0}, display{0, 0, 0, 0};
@@ -237,6 +238,7 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.il_count = ctx->il_count;
     p.il_index = ctx->il_index;
     p.skip_empty = ctx->grid_has_black_background ? 1u : 0u;
+    p.pool = ctx->ray_pool;
 }
 
 // after a grid became resident: does it have a black background worth skipping (>= 25 % black)?
@@ -549,6 +551,7 @@ int xn_ctx_create(int cuda_device, xn_ctx** out) {
         XN_CUDA(cudaEventCreate(&ctx->ev_mark[1]));
         XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
         XN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        XN_CUDA(cudaMalloc(&ctx->ray_pool, 256));
         for (int i = 0; i < 2; ++i) {
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -574,6 +577,7 @@ int xn_ctx_destroy(xn_ctx* ctx) {
         ctx->free_grid();
         ctx->free_nodes();
         if (ctx->own_target) cudaFree(ctx->own_target);
+        if (ctx->ray_pool) cudaFree(ctx->ray_pool);
         cudaEventDestroy(ctx->ev_start);
         cudaEventDestroy(ctx->ev_stop);
         if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);

@@ -117,6 +117,11 @@ struct FrameParams {
     // the colour arithmetic of warp-wide empty stretches
     uint32_t skip_empty;
 
+    // persistent ray pool (esvo_kernel<..., POOL>): counter of rays handed out, rays of this launch,
+    // 16-pixel block columns of the frame; nullptr = static one-thread-per-pixel launch
+    uint32_t* pool;
+    uint32_t pool_total, pool_blocks_x;
+
     uint32_t* steps_out;            // stats pass only
     unsigned long long* bytes_out;  // stats pass only
 };

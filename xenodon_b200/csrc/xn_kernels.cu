@@ -738,7 +738,24 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_TEX_MIN_BLOCKS) dda_tex_kern
 #endif
 // jump when a lane of the warp has at least this many steps of known texels ahead
 #ifndef XN_SKIP_JUMP_MIN
-#define XN_SKIP_JUMP_MIN 24
+#define XN_SKIP_JUMP_MIN 6
+#endif
+// 1 = a jump takes every step that ends before the promise does (the next trip fetches); 0 = it
+// stops a trip short of that, and a trip of known steps follows
+#ifndef XN_SKIP_FULL
+#define XN_SKIP_FULL 1
+#endif
+// look-up + jump rounds between two trips: after a jump the ray sits in the last promised voxel,
+// whose brick usually promises more
+#ifndef XN_SKIP_LOOK_TRIPS
+#define XN_SKIP_LOOK_TRIPS 2
+#endif
+#ifndef XN_SKIP_HOPS
+#define XN_SKIP_HOPS 1
+#endif
+// 1 = a jump may start while a fetched texel is pending (its length is kept in plen)
+#ifndef XN_SKIP_PLEN
+#define XN_SKIP_PLEN 1
 #endif
 // look the table up this many trips before the promise runs out
 #ifndef XN_SKIP_EARLY
@@ -833,6 +850,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
     TexAccum<STRICT> acc;
     uint32_t uc = 0;   // colour of the current promise
     float klen = 0.0f; // fast mode: length of known steps not yet added as uc * klen
+    float plen = 0.0f; // fast mode: length a jump gave the fetched texel still waiting in the pipeline
     if (!(t_min > t_max)) {
         t_min = gmax(t_min, 0.0f);
         ro = F3(ro.x + rd.x * t_min, ro.y + rd.y * t_min, ro.z + rd.z * t_min);
@@ -852,7 +870,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         const uint32_t osh = 8u * (oct & 3u);
         const float td_min = fminf(tdx, fminf(tdy, tdz));
         const float td45 = 4.5f * td_min;
-        const float td_look = 8.0f * td_min;                    // spacing floor of table look-ups (two trips)
+        const float td_look = (float)(4 * XN_SKIP_LOOK_TRIPS) * td_min; // spacing floor of table look-ups, in trips
         const float inv_trip = 0.999999f / (4.00390625f * td_min); // trips per unit of t, rounded down a little
         const float itdx = 1.0f / tdx, itdy = 1.0f / tdy, itdz = 1.0f / tdz;
         const float isum = (itdx + itdy) + itdz; // steps per unit of t
@@ -928,6 +946,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
                     acc.add(TexUniform<STRICT>::texel_of(uc), klen);                                               \
                     klen = 0.0f;                                                                                   \
                     if (pf == 0.0f) {                                                                              \
+                        if (plen != 0.0f) { /* PEND still holds a fetched texel that a jump closed */              \
+                            acc.add(PEND, plen);                                                                   \
+                            plen = 0.0f;                                                                           \
+                        }                                                                                          \
                         PEND = TexUniform<STRICT>::texel_of(uc);                                                   \
                         pf = 1.0f;                                                                                 \
                     }                                                                                              \
@@ -953,13 +975,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         const unsigned am = __activemask();                                                         \
         if (__any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                                      \
         if (!STRICT && XN_SKIP_BARE == 2) {                                                         \
+          _Pragma("unroll 1") for (int hop = 0; hop < XN_SKIP_HOPS; ++hop) {                         \
+            if (hop != 0 && __any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                      \
             /* every step that ends before T lands on a promised texel and leaves a whole trip before */ \
             /* the end of the ray: take them all at once, each lane its own T                        */ \
-            const float T = fminf(t_safe - td45, t_lim4);                                           \
-            const bool can = pf == 0.0f && t < T;                                                   \
-            if (__any_sync(am, can && (T - t) * isum >= (float)XN_SKIP_JUMP_MIN)) {                   \
+            const float T = fminf(XN_SKIP_FULL ? t_safe : t_safe - td45, t_lim4);                    \
+            /* a lane jumps if at least one step ends before T.  If the texel pending its segment was */ \
+            /* fetched (the trip before this fetched), the first of those steps closes it: its       */ \
+            /* length goes to plen, which the next trip adds when it consumes that texel -- so a     */ \
+            /* ray goes from fetching to jumping without a trip of known steps in between            */ \
+            const float tfirst = fminf(sdx, fminf(sdy, sdz));                                       \
+            const bool can = tfirst < T && (XN_SKIP_PLEN || pf == 0.0f);                            \
+            if (!__any_sync(am, can && (T - t) * isum >= (float)XN_SKIP_JUMP_MIN)) break;             \
+            {                                                                                       \
                 if (can) {                                                                          \
                     float tl = t, kx = 0.0f, ky = 0.0f, kz = 0.0f;                                  \
+                    float tb = t;                                                                   \
+                    if (XN_SKIP_PLEN && pf != 0.0f) {                                               \
+                        plen = tfirst - t;                                                          \
+                        tb = tfirst;                                                                \
+                        pf = 0.0f;                                                                  \
+                    }                                                                               \
                     if (STATS) {                                                                    \
                         /* the instrumented build takes the same steps one by one (counting them) */ \
                         /* and checks the closed form against them: a mismatch poisons the count  */ \
@@ -988,10 +1024,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
                     fx = __fmaf_rn(sg.x, kx, fx);                                                   \
                     fy = __fmaf_rn(sg.y, ky, fy);                                                   \
                     fz = __fmaf_rn(sg.z, kz, fz);                                                   \
-                    klen += tl - t;                                                                 \
+                    klen += tl - tb;                                                                \
                     t = tl;                                                                         \
                 }                                                                                   \
             }                                                                                       \
+          }                                                                                         \
         } else if (!STRICT && XN_SKIP_BARE == 1) {                                                  \
             /* trips certain to be known: the k-th starts before t + 4 k td_min (1 + 2^-10), and must  */ \
             /* start before min(t_safe, t_end) - 4.5 td_min; +1 because trip 0 starts at t itself; a */ \
@@ -1039,7 +1076,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
         acc.add(P##0, P##d1);                               \
         acc.add(P##1, P##d2);                               \
         acc.add(P##2, P##d3);                               \
-        acc.add(P##3, d0);                                  \
+        acc.add(P##3, STRICT ? d0 : d0 + plen);             \
+        plen = 0.0f;                                        \
     }
 #define XN_SKIP_FLUSH(P)       \
     {                          \
@@ -1064,6 +1102,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
             }
         }
         // the last few steps, one at a time (the promise in force still applies)
+        if (!STRICT && plen != 0.0f) {
+            acc.add(v, plen);
+            plen = 0.0f;
+        }
         while (t < t_end) {
             float dt;
             texel vn = v;
@@ -1620,6 +1662,36 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
     store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
 }
 
+// ---------------------------------------------------------------------------------
+// Persistent-thread ray pool.  p.pool[0] counts the rays handed out in this launch (zeroed by the
+// launcher); ray id -> pixel keeps the static launch's shape: 32 consecutive ids are one warp's
+// 8x4 tile, BLOCK_THREADS ids one 16-row block, blocks row-major over the owned stripes.
+// Idle lanes of a warp are served together: one atomic for the warp, offsets from the ballot.
+// Returns true on the lanes that received a ray inside the frame; `dry` turns true (for the
+// whole warp) once the counter has passed the last ray.
+// ---------------------------------------------------------------------------------
+#ifndef XN_POOL_MIN_ACTIVE
+#define XN_POOL_MIN_ACTIVE 24
+#endif
+__device__ __forceinline__ bool ray_pool_draw(const FrameParams& p, bool idle, bool& dry, uint32_t& ix, uint32_t& iy) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, idle);
+    if (m == 0u || dry) return false;
+    const uint32_t lane = threadIdx.x & 31u, n = (uint32_t)__popc(m);
+    const int leader = __ffs((int)m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(p.pool, n);
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    dry = base + n >= p.pool_total;
+    if (!idle) return false;
+    const uint32_t id = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    if (id >= p.pool_total) return false;
+    const uint32_t blk = id / (uint32_t)BLOCK_THREADS, in = id % (uint32_t)BLOCK_THREADS, w = in >> 5, l = in & 31u;
+    const uint32_t bx = blk % p.pool_blocks_x, by = blk / p.pool_blocks_x;
+    ix = bx * BLOCK_W + (w % BLOCK_WARPS_X) * TILE_W + l % TILE_W;
+    iy = (by * p.il_count + p.il_index) * BLOCK_H + (w / BLOCK_WARPS_X) * TILE_H + l / TILE_W;
+    return ix < p.out_w && iy < p.out_h;
+}
+
 // ESVO child selection.  The compiler turns `if (c) { pos += d; idx ^= bit; }` into compare +
 // FADD + FSEL + SEL chains on the ALU pipe, which bounded this kernel (ncu: ALU 70 %, issue 72 %).
 // XN_ESVO_PTX = 2 writes the comparisons as 1.0 / 0.0 flags (`set`) followed by exact FMAs, which
@@ -1696,20 +1768,60 @@ __device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, f
 // The reference indexes its stacks by `scale` (22 downwards); here level = 22 - scale, so
 // LEVELS (>= tree depth) levels of shared memory are enough.
 // ---------------------------------------------------------------------------------
-template <bool STATS, bool STRICT, int LEVELS>
+//
+// POOL (north_star's persistent-thread ray pool, after Aila & Laine 2009): the grid is one wave of
+// resident blocks whose warps draw rays from a per-launch counter (ray_pool_draw: one atomic per
+// warp and refill, lane offsets from the ballot of idle lanes) until it runs dry.  A warp leaves
+// the traversal loop to refill when fewer than XN_POOL_MIN_ACTIVE of its lanes still have a ray;
+// lanes that kept theirs re-enter the loop with their state untouched (the stack is per thread, not
+// per ray slot).  Rays are numbered so that 32 consecutive ones are an 8x4 tile and 256 a block of
+// the static launch: a freshly filled warp is as coherent as a static one.  What it buys is
+// measured, not assumed: profiles/README.md (ray pool).
+template <bool STATS, bool STRICT, int LEVELS, bool POOL = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_ESVO_MIN_BLOCKS) esvo_kernel(const __grid_constant__ FrameParams p) {
     // [scale][thread] = (parent, bits(t_max)).  Trees this instantiation is launched for are shallower
     // than LEVELS; the index is clamped instead of bounds-tested, so a malformed file (a cycle of
     // child pointers) aliases its own thread's last entry and nothing else.  Shared memory is
     // kept small on purpose: what the stacks take is carved out of the L1 cache.
     __shared__ uint2 stack_mem[LEVELS * BLOCK_THREADS];
-    uint32_t ix, iy;
-    thread_pixel(p, ix, iy);
-    if (ix >= p.out_w || iy >= p.out_h) return;
-    RayStats<STATS> st;
     const uint32_t cast_stack_depth = 23u;
-
-    const f3 rd = make_ray(p, p.out_x + (int32_t)ix, p.out_y + (int32_t)iy);
+    uint32_t ix = 0, iy = 0;
+    if (!POOL) {
+        thread_pixel(p, ix, iy);
+        if (ix >= p.out_w || iy >= p.out_h) return;
+    }
+    RayStats<STATS> st;
+    // POOL: everything a ray carries is declared out here so that a lane keeps it across refills
+    f3 rd = F3(0.f, 0.f, 0.f);
+    float tcx = 0.f, tcy = 0.f, tcz = 0.f, tbx = 0.f, tby = 0.f, tbz = 0.f, t_min = 0.f, t_max = 0.f;
+    float posx = 1.f, posy = 1.f, posz = 1.f, scale_exp2 = 0.5f;
+    uint32_t octant_mask = 0, parent = 0, idx = 0, s = 0;
+    uint32_t scale = cast_stack_depth; // >= cast_stack_depth: this lane has no ray
+#if !XN_ESVO_ALWAYS_STORE
+    float h = 0.f;
+#endif
+    Accum<STRICT> acc;
+    bool dry = false;  // POOL: the counter has passed the last ray (warp-uniform)
+    bool have = false; // POOL: this lane holds a ray
+    constexpr uint32_t MIN_SCALE = LEVELS >= 23 ? 0u : 23u - (uint32_t)LEVELS;
+    const uint32_t stack = stack_base(stack_mem) - MIN_SCALE * (uint32_t)(BLOCK_THREADS * sizeof(uint2));
+    const CNode* __restrict__ nodes = p.cnodes;
+  for (;;) {
+    bool fresh = !POOL;
+    if (POOL) {
+        fresh = ray_pool_draw(p, !have, dry, ix, iy);
+        if (__all_sync(0xFFFFFFFFu, !have && !fresh)) {
+            if (dry) return;
+            continue; // every ray drawn fell outside the frame: draw again
+        }
+    }
+    if (fresh) {
+    if (POOL) {
+        st = RayStats<STATS>();
+        acc = Accum<STRICT>();
+        have = true;
+    }
+    rd = make_ray(p, p.out_x + (int32_t)ix, p.out_y + (int32_t)iy);
     f3 ro = F3(p.pos[0] + 1.0f, p.pos[1] + 1.0f, p.pos[2] + 1.0f);
     {
         // aabb_intersect(vec3(1), vec3(2), ro, rd), esvo.comp:10-21
@@ -1722,42 +1834,42 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_ESVO_MIN_BLOCKS) esvo_kernel
         ro = F3(ro.x + adv * rd.x, ro.y + adv * rd.y, ro.z + adv * rd.z);
     }
 
-    const float tcx = 1.0f / -fabsf(rd.x), tcy = 1.0f / -fabsf(rd.y), tcz = 1.0f / -fabsf(rd.z);
-    float tbx = tcx * ro.x, tby = tcy * ro.y, tbz = tcz * ro.z;
-    uint32_t octant_mask = 0;
+    tcx = 1.0f / -fabsf(rd.x), tcy = 1.0f / -fabsf(rd.y), tcz = 1.0f / -fabsf(rd.z);
+    tbx = tcx * ro.x, tby = tcy * ro.y, tbz = tcz * ro.z;
+    octant_mask = 0;
     if (rd.x > 0.0f) { tbx = 3.0f * tcx - tbx; octant_mask ^= 4u; }
     if (rd.y > 0.0f) { tby = 3.0f * tcy - tby; octant_mask ^= 2u; }
     if (rd.z > 0.0f) { tbz = 3.0f * tcz - tbz; octant_mask ^= 1u; }
 
-    float t_min = max_elem(F3(2.0f * tcx - tbx, 2.0f * tcy - tby, 2.0f * tcz - tbz));
-    float t_max = min_elem(F3(tcx - tbx, tcy - tby, tcz - tbz));
+    t_min = max_elem(F3(2.0f * tcx - tbx, 2.0f * tcy - tby, 2.0f * tcz - tbz));
+    t_max = min_elem(F3(tcx - tbx, tcy - tby, tcz - tbz));
 #if !XN_ESVO_ALWAYS_STORE
-    float h = t_max;
+    h = t_max;
 #endif
     t_min = gmax(t_min, 0.0f);
     t_max = gmin(t_max, sqrtf(3.0f));
 
-    uint32_t parent = 0, idx = 0;
-    float posx = 1.f, posy = 1.f, posz = 1.f;
-    uint32_t scale = cast_stack_depth - 1u;
-    float scale_exp2 = 0.5f;
+    parent = 0, idx = 0;
+    posx = 1.f, posy = 1.f, posz = 1.f;
+    scale = cast_stack_depth - 1u;
+    scale_exp2 = 0.5f;
     if (1.5f * tcx - tbx > t_min) { posx = 1.5f; idx ^= 4u; }
     if (1.5f * tcy - tby > t_min) { posy = 1.5f; idx ^= 2u; }
     if (1.5f * tcz - tbz > t_min) { posz = 1.5f; idx ^= 1u; }
 
-    Accum<STRICT> acc;
     // entries are indexed by `scale` itself, as in esvo.comp:34-35: the base is moved down by the
     // (23 - LEVELS) scales this instantiation never reaches, so a push / pop address is one scaled add
-    constexpr uint32_t MIN_SCALE = LEVELS >= 23 ? 0u : 23u - (uint32_t)LEVELS;
-    const uint32_t stack = stack_base(stack_mem) - MIN_SCALE * (uint32_t)(BLOCK_THREADS * sizeof(uint2));
-    const CNode* __restrict__ nodes = p.cnodes;
 
     // The child descriptor of (parent, idx) is requested at the END of the previous iteration,
     // at a single load site (99.6 % of iterations consume it, ncu r01), so the t_corner
     // arithmetic of the next iteration overlaps the load instead of waiting behind it.
-    uint32_t s = load_word(nodes, parent, idx ^ octant_mask);
+    s = load_word(nodes, parent, idx ^ octant_mask);
+    } // ray set-up
 
+    if (!POOL || have) {
     while (scale < cast_stack_depth) {
+        // POOL: too few lanes left with a ray -> out to the refill (this lane keeps its state)
+        if (POOL && !dry && __popc(__activemask()) < XN_POOL_MIN_ACTIVE) break;
         st.step();
         const float tcorx = posx * tcx - tbx, tcory = posy * tcy - tby, tcorz = posz * tcz - tbz;
         const float tc_max = fminf(tcorx, fminf(tcory, tcorz));
@@ -1852,7 +1964,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_ESVO_MIN_BLOCKS) esvo_kernel
         }
         s = load_word(nodes, parent, idx ^ octant_mask);
     }
-    store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
+    if (!POOL || scale >= cast_stack_depth) {
+        store_result(p, ix, iy, acc.finish(voxel_emission_coeff(p, rd)), st);
+        have = false;
+    }
+    }
+    if (!POOL) return;
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -2070,6 +2188,12 @@ static bool force_idx64() {
     return v;
 }
 
+// XN_RAY_POOL=1: the ESVO draws its rays from the persistent pool (measured: profiles/README.md)
+static bool ray_pool_mode() {
+    const char* e = getenv("XN_RAY_POOL"); // read per launch: tests and A/B runs flip it inside one process
+    return e && e[0] == '1';
+}
+
 template <bool STATS, bool STRICT>
 static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t stream) {
     const uint32_t stripes = (p.out_h + BLOCK_H - 1) / BLOCK_H;
@@ -2099,6 +2223,25 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
             break;
         case 1: svo_naive_kernel<STATS, STRICT><<<grid, block, 0, stream>>>(p); break;
         case 2:
+            if (p.pool && ray_pool_mode() && !deep) {
+                // persistent grid: one wave of resident blocks drawing from the pool
+                static int per_sm = 0, sms = 0;
+                if (per_sm == 0) {
+                    int dev = 0;
+                    cudaGetDevice(&dev);
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, esvo_kernel<false, false, 12, true>, BLOCK_THREADS, 0);
+                    if (per_sm <= 0) per_sm = 1;
+                }
+                FrameParams q = p;
+                q.pool_blocks_x = grid.x;
+                q.pool_total = grid.x * grid.y * (uint32_t)BLOCK_THREADS;
+                cudaError_t e = cudaMemsetAsync(q.pool, 0, sizeof(uint32_t), stream);
+                if (e != cudaSuccess) return e;
+                const uint32_t blocks = min((uint32_t)(per_sm * sms), grid.x * grid.y);
+                esvo_kernel<STATS, STRICT, 12, true><<<blocks, block, 0, stream>>>(q);
+                break;
+            }
             if (deep) esvo_kernel<STATS, STRICT, 24><<<grid, block, 0, stream>>>(p);
             else esvo_kernel<STATS, STRICT, 12><<<grid, block, 0, stream>>>(p);
             break;

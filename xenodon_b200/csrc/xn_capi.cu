@@ -262,7 +262,9 @@ void classify_grid(xn_ctx* ctx) {
     ctx->skip_table = nullptr;
     const char* on = std::getenv("XN_DDA_SKIP");
     if (on && on[0] == '0') return;
-    uint32_t shift = 3, cap = 32;
+    // brick edge: 8 voxels; 4 on the volumes far beyond L2 (a finer table finds more uniform bricks
+    // between the filaments of the gas volumes: cfg3 +7 %, cfg4 +2 %; on the bunny shape it costs 3 %)
+    uint32_t shift = n >= (1ull << 29) ? 2 : 3, cap = 32;
     if (const char* s = std::getenv("XN_SKIP_SHIFT")) shift = (uint32_t)std::strtoul(s, nullptr, 10);
     if (const char* s = std::getenv("XN_SKIP_CAP")) cap = (uint32_t)std::strtoul(s, nullptr, 10);
     if (ctx->nx > 0x7FFFFFu || ctx->ny > 0x7FFFFFu || ctx->nz > 0x7FFFFFu) return; // texel centres exact below 2^23

@@ -747,8 +747,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_TEX_MIN_BLOCKS) dda_tex_kern
 #endif
 // look-up + jump rounds between two trips: after a jump the ray sits in the last promised voxel,
 // whose brick usually promises more
+// 1 = trips always fetch (known texels included: with the jump taking the known stretches, 0.1 % of
+// the steps; the known / fetched bookkeeping of every step costs more than those fetches: cfg4
+// 1504 -> 1714); 0 = a trip that starts well inside a promise does not fetch
+#ifndef XN_SKIP_TRIP_FETCH
+#define XN_SKIP_TRIP_FETCH 1
+#endif
 #ifndef XN_SKIP_LOOK_TRIPS
-#define XN_SKIP_LOOK_TRIPS 2
+#define XN_SKIP_LOOK_TRIPS 3
 #endif
 #ifndef XN_SKIP_HOPS
 #define XN_SKIP_HOPS 1
@@ -802,15 +808,13 @@ struct TexUniform<true> {
 // (s, d, T) including tie-prone d: tools/jump_proto.py.)
 __device__ __forceinline__ void dda_axis_jump(float& s, const float d, const float T, float& t_last, float& kf) {
     while (s < T) {
-        t_last = fmaxf(t_last, s);
-        s += d;
-        kf += 1.0f;
-        if (!(s < T)) break;
-        const float q = (s + d) - s;
+        const float s1 = s + d, q = s1 - s; // one real addition: the next crossing, and the increment
         const uint32_t sb = __float_as_uint(s), eb = sb & 0x7F800000u;
         const float top = __uint_as_float(eb + 0x00800000u);    // 2^(e+1)
         const float half_u = __uint_as_float(eb - (24u << 23)); // 2^(e-24)
-        if (s + d < top && (fabsf(d - q) != half_u || (sb & 1u) == 0u)) {
+        if (s1 < top && (fabsf(d - q) != half_u || (sb & 1u) == 0u)) {
+            // s, s + q, ... below hi = min(T, 2^(e+1)) are all crossings taken; the one after the
+            // last of them is a real addition again (it may leave the binade, or pass T)
             const float hi = fminf(T, top);
             float jf = floorf(__fdividef(hi - s, q) * 0.99999f);
             float sj = __fmaf_rn(jf, q, s);
@@ -818,8 +822,13 @@ __device__ __forceinline__ void dda_axis_jump(float& s, const float d, const flo
                 sj += q;
                 jf += 1.0f;
             }
-            s = sj;
-            kf += jf;
+            t_last = fmaxf(t_last, sj);
+            s = sj + d;
+            kf += jf + 1.0f;
+        } else {
+            t_last = fmaxf(t_last, s);
+            s = s1;
+            kf += 1.0f;
         }
     }
 }
@@ -902,14 +911,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
     }
         // One step inside a trip.  The step's length belongs to the texel requested by the PREVIOUS
         // step: FP = 1.0 if that one was fetched (DT = length) or 0.0 if it is known (length -> klen).
-        // FETCH (constant over the trip): request the texel of the voxel stepped into.
-#define XN_SKIP_STEP(DT, FP, TEXEL, FETCH)                         \
+        // FETCH (constant over the trip): request the texel of the voxel stepped into.  PLAIN: the
+        // previous texel is certainly a fetched one (no known-length bookkeeping).
+#define XN_SKIP_STEP(DT, FP, TEXEL, FETCH, PLAIN)                  \
     {                                                              \
         float dt_;                                                 \
         XN_SKIP_GEOM(dt_)                                          \
         st.step();                                                 \
         if (!XN_SKIP_DEBUG) st.read(4);                            \
-        if (STRICT) {                                              \
+        if (STRICT || PLAIN) {                                     \
             DT = dt_;                                              \
         } else {                                                   \
             DT = dt_ * FP;                                         \
@@ -1065,13 +1075,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
     }
 #define XN_SKIP_TRIP(N, P)                                  \
     {                                                       \
-        const bool fetch = !(t < t_safe - td45);            \
+        const bool fetch = XN_SKIP_TRIP_FETCH || !(t < t_safe - td45); \
         const float nf = fetch ? 1.0f : 0.0f;               \
         float d0;                                           \
-        XN_SKIP_STEP(d0, pf, N##0, fetch)                   \
-        XN_SKIP_STEP(N##d1, nf, N##1, fetch)                \
-        XN_SKIP_STEP(N##d2, nf, N##2, fetch)                \
-        XN_SKIP_STEP(N##d3, nf, N##3, fetch)                \
+        XN_SKIP_STEP(d0, pf, N##0, fetch, false)            \
+        XN_SKIP_STEP(N##d1, nf, N##1, fetch, XN_SKIP_TRIP_FETCH) \
+        XN_SKIP_STEP(N##d2, nf, N##2, fetch, XN_SKIP_TRIP_FETCH) \
+        XN_SKIP_STEP(N##d3, nf, N##3, fetch, XN_SKIP_TRIP_FETCH) \
         pf = nf;                                            \
         acc.add(P##0, P##d1);                               \
         acc.add(P##1, P##d2);                               \

@@ -10,6 +10,10 @@ cap() { # workload traversal kernel-regex name launch-skip
   ncu --set full --clock-control none --import-source on -k regex:$3 --launch-skip $5 --launch-count 1 -f \
     -o gpurun_out/${TAG}_$4 python bench.py --workload $1 --traversal $2 --no-extras --steps 20 --warmup 3 > gpurun_out/${TAG}_$4.log 2>&1
   ncu -i gpurun_out/${TAG}_$4.ncu-rep --page raw --csv > gpurun_out/${TAG}_$4_ncu_raw.csv 2>/dev/null
+  # per-instruction execution and lane counts (tools/sass_segments.py reads these)
+  ncu -i gpurun_out/${TAG}_$4.ncu-rep --page source --csv --print-source sass > gpurun_out/${TAG}_$4_sass.csv 2>/dev/null
+  # gpurun brings back at most 64 MiB: keep the reports of the two headline kernels only
+  case $4 in dda_cfg4_f120|esvo_f120) ;; *) rm -f gpurun_out/${TAG}_$4.ncu-rep ;; esac
 }
 # launch-skip = 3 warm-up launches + step index; step s of 20 renders script frame floor(s * 150 / 20):
 # step 2 = frame 15 (outside, distance 2), step 16 = frame 120 (inside the volume)
@@ -17,13 +21,14 @@ cap cfg4 dda dda_ dda_cfg4_f15 5
 cap cfg4 dda dda_ dda_cfg4_f120 19
 cap cfg3 dda dda_ dda_cfg3_f120 19
 cap cfg1 dda dda_ dda_cfg1 5
+cap cfg2 dda dda_ dda_cfg2 19
 cap cfg2 esvo esvo_kernel esvo_f15 5
 cap cfg2 esvo esvo_kernel esvo_f120 19
 cap cfg4e esvo esvo_kernel esvo_cfg4e_f120 19
-cap cfg2 svo-df svo_df_kernel df_f15 5
-cap cfg2 svo-rope svo_rope rope_f15 5
+cap cfg2 svo-df svo_df df_f120 19
+cap cfg2 svo-rope svo_rope rope_f120 19
 cap cfg3r svo-rope svo_rope rope_cfg3r_f120 19
-cap cfg2 svo-naive svo_naive_kernel naive_f15 5
+cap cfg2 svo-naive svo_naive_kernel naive_f120 19
 # un-profiled bench lines: the driver's command, longer runs of every workload, the reference arm
 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err

@@ -86,6 +86,17 @@ struct RayStats {
     }
 };
 
+// One 256-bit read-only load of a 32-byte, 32-byte-aligned record (sm_100: LDG.E.256): one request
+// and one sector per lane where two 128-bit loads are two requests for the same sector.
+#ifndef XN_LDG256
+#define XN_LDG256 1
+#endif
+__device__ __forceinline__ void ldg256(const void* ptr, uint4& lo, uint4& hi) {
+    asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+        : "l"(ptr));
+}
+
 // (float)byte k of v, exactly, on the ALU/FMA pipes: 0x4B0000bb is 2^23 + bb
 template <int K>
 __device__ __forceinline__ float byte_f(uint32_t v) {
@@ -1456,8 +1467,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SVO_MIN_BLOCKS) svo_df_kerne
         // of the loop enters exactly one node, with the whole warp on the plane arithmetic.
         for (;;) {
             df_planes(P, side, rrd, bias, q);
+#if XN_LDG256
+            uint4 w0, w1;
+            ldg256(reinterpret_cast<const uint32_t*>(p.cnodes) + node, w0, w1);
+#else
             const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.cnodes) + node));
             const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.cnodes) + node) + 1);
+#endif
             const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             uint32_t inner = 0, hits = 0;
 #pragma unroll
@@ -2069,10 +2085,14 @@ struct RRec {
     uint4 a, b; // w[0..3], w[4..7]
 };
 __device__ __forceinline__ RRec load_rrec(const RNode* __restrict__ nodes, uint32_t i) {
-    const uint4* q = reinterpret_cast<const uint4*>(nodes + i);
     RRec r;
+#if XN_LDG256
+    ldg256(nodes + i, r.a, r.b);
+#else
+    const uint4* q = reinterpret_cast<const uint4*>(nodes + i);
     r.a = __ldg(q);
     r.b = __ldg(q + 1);
+#endif
     return r;
 }
 __device__ __forceinline__ uint32_t rrec_word(const RRec& r, uint32_t k) { // k in 0..7, runtime

@@ -765,10 +765,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_TEX_MIN_BLOCKS) dda_tex_kern
 #define XN_SKIP_TRIP_FETCH 1
 #endif
 #ifndef XN_SKIP_LOOK_TRIPS
-#define XN_SKIP_LOOK_TRIPS 3
+#define XN_SKIP_LOOK_TRIPS 4
 #endif
 #ifndef XN_SKIP_HOPS
 #define XN_SKIP_HOPS 1
+#endif
+// rounds after the first need this many lanes of the warp able to jump (1 = any lane)
+#ifndef XN_SKIP_HOP_LANES
+#define XN_SKIP_HOP_LANES 1
 #endif
 // 1 = a jump may start while a fetched texel is pending (its length is kept in plen)
 #ifndef XN_SKIP_PLEN
@@ -1007,7 +1011,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
             /* ray goes from fetching to jumping without a trip of known steps in between            */ \
             const float tfirst = fminf(sdx, fminf(sdy, sdz));                                       \
             const bool can = tfirst < T && (XN_SKIP_PLEN || pf == 0.0f);                            \
-            if (!__any_sync(am, can && (T - t) * isum >= (float)XN_SKIP_JUMP_MIN)) break;             \
+            /* the first round jumps if any lane can; a further round before the next trip only if */ \
+            /* at least XN_SKIP_HOP_LANES lanes can (the others would wait for them)               */ \
+            const unsigned cm = __ballot_sync(am, can && (T - t) * isum >= (float)XN_SKIP_JUMP_MIN);  \
+            if (hop == 0 ? cm == 0u : __popc(cm) < XN_SKIP_HOP_LANES) break;                        \
             {                                                                                       \
                 if (can) {                                                                          \
                     float tl = t, kx = 0.0f, ky = 0.0f, kz = 0.0f;                                  \

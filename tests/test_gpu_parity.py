@@ -430,6 +430,25 @@ def test_deep_trees_use_the_deep_stack_instantiation(xb, xo, traversal, depth):
                  emission=1.0)
 
 
+@pytest.mark.parametrize("bricks", ["1", "0"])
+@pytest.mark.parametrize("cam", ["orbit", "inside", "oblique", "aniso"])
+def test_esvo_leaf_bricks_match_oracle(xb, xo, cam, bricks, monkeypatch):
+    """The fast-mode ESVO integrates a node whose eight children are all leaves in closed form (the
+    three centre-plane crossings, sorted) instead of descending into it; XN_ESVO_BRICKS=0 keeps the
+    child-by-child loop.  Both stay within 1/255 of the oracle, the strict mode stays bit-identical,
+    and the instrumented pass still reports the shader's loop counts.  Volumes: voxel noise (every
+    bottom-level node is a brick), blobs (bricks at the surfaces only), and a DAG (shared bricks)."""
+    monkeypatch.setenv("XN_ESVO_BRICKS", bricks)
+    rng = np.random.default_rng(len(cam) * 11 + 3)
+    kw = dict(camera=CAMERAS[cam], output=(0, 0, 203, 117), display=(0, 0, 203, 117), emission=2.0)
+    if cam == "aniso":
+        kw["ratio"] = (1.0, 2.0, 0.5)
+    for g, type_ in ((random_grid(rng, 32, 32, 32), xb.TYPE_SPARSE), (blobby_grid(rng, 64, 45, 64), xb.TYPE_SPARSE),
+                     (blobby_grid(rng, 40, 29, 33), xb.TYPE_DAG)):
+        tree, _ = xb.build_octree(xb.Grid(g), chan_diff=0, type=type_)
+        _compare(xb, xo, "esvo", tree=tree, **kw)
+
+
 @pytest.mark.parametrize("cam", ["orbit", "inside", "oblique", "single"])
 def test_esvo_ray_pool_matches_oracle(xb, xo, cam, monkeypatch):
     """XN_RAY_POOL=1: the ESVO's warps draw their rays from a persistent pool (one resident wave of

@@ -108,6 +108,7 @@ struct xn_ctx {
     uint32_t* top_table = nullptr; // svo_naive entry table
     uint32_t top_levels = 0;
     uint64_t node_count = 0, internal_count = 0, side = 0;
+    uint32_t brick_base = 0xFFFFFFFFu; // word offset of the first leaf-brick record in cnodes
     uint32_t root_meta = 0, max_depth = 0;
     bool grid_has_black_background = false;
     uint4* skip_table = nullptr; // DDA skip table of the resident grid (any layout)
@@ -162,6 +163,7 @@ struct xn_ctx {
         cnodes = nullptr;
         top_table = nullptr;
         node_count = internal_count = side = 0;
+        brick_base = 0xFFFFFFFFu;
     }
 };
 
@@ -231,6 +233,11 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.nodes = ctx->nodes;
     p.rnodes = ctx->rnodes;
     p.cnodes = ctx->cnodes;
+    {
+        // XN_ESVO_BRICKS=0: the fast-mode ESVO descends into leaf bricks child by child, as the strict mode does
+        const char* e = std::getenv("XN_ESVO_BRICKS");
+        p.brick_base = (e && e[0] == '0') ? 0xFFFFFFFFu : ctx->brick_base;
+    }
     p.top_table = ctx->top_table;
     p.top_levels = ctx->top_levels;
     p.root_meta = ctx->root_meta;
@@ -472,7 +479,7 @@ void finish_svo_upload(xn_ctx* ctx, void* d_raw, uint64_t count, uint64_t side) 
         XN_CUDA(xn::launch_relayout(d_raw, count, ctx->nodes, ctx->stream));
     }
     {
-        const cudaError_t e = xn::build_compact_nodes(d_raw, count, &ctx->cnodes, &ctx->internal_count, ctx->stream);
+        const cudaError_t e = xn::build_compact_nodes(d_raw, count, &ctx->cnodes, &ctx->internal_count, &ctx->brick_base, ctx->stream);
         if (e == cudaErrorInvalidValue) {
             cudaGetLastError();
             ctx->free_nodes();

@@ -102,6 +102,9 @@ struct FrameParams {
     const DNode* nodes;   // svo_rope (and the file-order view of the tree)
     const RNode* rnodes;  // svo_rope, 32-byte records (nullptr: the tree exceeds their limits, nodes is read)
     const CNode* cnodes;  // svo_naive, svo_df, esvo
+    // child words at or above this word offset name leaf bricks: records whose eight children are all
+    // leaves (sorted behind the other internal nodes); 0xFFFFFFFF = none / not used
+    uint32_t brick_base;
     // svo_naive: what find() reaches after its first top_levels levels, for each of the
     // 2^(3 top_levels) aligned cells of the cube (a leaf word, or the word offset of an internal
     // node), index = cx << 2 top_levels | cy << top_levels | cz; top_levels = min(tree depth, 8)

@@ -1796,6 +1796,42 @@ __device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, f
 #endif
 }
 
+// Leaf brick (fast mode only).  The child `s` of the current node is an internal node whose eight
+// children are all leaves: instead of PUSHing into it and visiting its children one loop iteration
+// each (two to four iterations of PUSH / ADVANCE / POP at the lane divergence of the deepest level,
+// where neighbouring rays are in different phases all the time), its share of the integral is taken
+// here in closed form.  In the mirrored frame the ray leaves the upper half of every axis when it
+// crosses the node's centre plane at tcen_i = (pos_i + half) tc_i - tb_i; clipped to the ray's stay
+// [t_min, t_end] in the node and sorted, the three crossings cut the stay into at most four chords,
+// and the child that holds a chord has its bit set on exactly the axes whose crossing is still
+// ahead.  These are the chords esvo.comp:65-104 walks through (a child's exit time is the next
+// crossing), up to the rounding of t -- which is why the strict mode keeps the loop.  Chords of
+// length zero (a plane crossed outside the stay, or two at once) add colour x 0.
+#ifndef XN_ESVO_BRICKS
+#define XN_ESVO_BRICKS 1
+#endif
+template <bool STRICT>
+__device__ __forceinline__ void esvo_leaf_brick(const CNode* __restrict__ nodes, uint32_t s, uint32_t octant_mask,
+                                                float tcx, float tcy, float tcz, float tcorx, float tcory, float tcorz,
+                                                float half, float t_min, float t_end, Accum<STRICT>& acc) {
+    const float ax = fminf(fmaxf(__fmaf_rn(half, tcx, tcorx), t_min), t_end);
+    const float ay = fminf(fmaxf(__fmaf_rn(half, tcy, tcory), t_min), t_end);
+    const float az = fminf(fmaxf(__fmaf_rn(half, tcz, tcorz), t_min), t_end);
+    const float lo = fminf(ax, ay), hi = fmaxf(ax, ay);
+    const float t1 = fminf(lo, az), t3 = fmaxf(hi, az), t2 = fmaxf(lo, fminf(hi, az));
+    // child holding the chord that starts at ts: upper half on the axes not yet crossed
+#define XN_BRICK_CHILD(ts) ((ax > (ts) ? 4u : 0u) | (ay > (ts) ? 2u : 0u) | (az > (ts) ? 1u : 0u))
+    const uint32_t w0 = load_word(nodes, s, XN_BRICK_CHILD(t_min) ^ octant_mask);
+    const uint32_t w1 = load_word(nodes, s, XN_BRICK_CHILD(t1) ^ octant_mask);
+    const uint32_t w2 = load_word(nodes, s, XN_BRICK_CHILD(t2) ^ octant_mask);
+    const uint32_t w3 = load_word(nodes, s, octant_mask); // every plane crossed: the lowest child
+#undef XN_BRICK_CHILD
+    acc.add(w0, t1 - t_min);
+    acc.add(w1, t2 - t1);
+    acc.add(w2, t3 - t2);
+    acc.add(w3, t_end - t3);
+}
+
 // ---------------------------------------------------------------------------------
 // esvo (resources/esvo.comp:10-157)
 // The reference indexes its stacks by `scale` (22 downwards); here level = 22 - scale, so
@@ -1917,6 +1953,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_ESVO_MIN_BLOCKS) esvo_kernel
                 if (word_is_leaf(s)) {
                     st.read(4); // color
                     acc.add(s, tv_max - t_min);
+                } else if (XN_ESVO_BRICKS && !STATS && !STRICT && s >= p.brick_base) {
+                    // eight leaves below: integrated here, then ADVANCE as after a leaf
+                    esvo_leaf_brick(nodes, s, octant_mask, tcx, tcy, tcz, tcorx, tcory, tcorz, scale_exp2 * 0.5f, t_min,
+                                    tv_max, acc);
                 } else {
                     // PUSH.  esvo.comp:79-82 skips the stack write when the child's exit time is not
                     // below `h` (the parent will never be popped to); writing always stores the

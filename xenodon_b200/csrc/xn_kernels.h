@@ -13,6 +13,7 @@ cudaError_t launch_max_depth(const void* raw40, uint64_t count, uint32_t* d_max_
 cudaError_t launch_relayout_rnodes(const void* raw40, uint64_t count, RNode* out, cudaStream_t stream);
 // compact residency of the octree (internal nodes only, level order); *out is cudaMalloc'ed
 cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, uint64_t* n_internal_out,
+                                uint32_t* brick_base_out,
                                 cudaStream_t stream);
 // svo_naive entry table (2^(3 levels) words)
 cudaError_t launch_top_table(const CNode* nodes, uint32_t root_meta, uint32_t levels, uint32_t* table,

@@ -89,24 +89,36 @@ cudaError_t launch_relayout(const void* raw40, uint64_t count, DNode* out, cudaS
 
 // ---------------------------------------------------------------------------------
 // compact octree residency (CNode, xn_device.cuh): internal nodes only, level order.
-//   1. key = depth for internal nodes (root forced to 0), 31 for leaves; stable radix sort of
-//      the node indices by key  ->  level order with file order inside a level, leaves last;
+//   1. key = depth for internal nodes (root forced to 0), 30 for leaf bricks (internal nodes whose
+//      eight children are all leaves), 31 for leaves; stable radix sort of the node indices by key
+//      ->  level order with file order inside a level, then the leaf bricks, leaves last: a child
+//      word at or above *brick_base_out (a word offset) names a leaf brick, no flag bit needed;
 //   2. rank[file index] = position in that order (the compact index);
 //   3. one thread per internal node writes its eight child words.
 // ---------------------------------------------------------------------------------
 __global__ void compact_keys_kernel(const uint32_t* __restrict__ raw, uint64_t count, uint8_t* __restrict__ keys,
                                     uint32_t* __restrict__ vals, unsigned long long* __restrict__ n_internal) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned internal = 0;
+    unsigned internal = 0, brick = 0;
     if (i < count) {
         const uint32_t ld = raw[i * 10u + 9u];
         const bool leaf = (ld & 0x80000000u) != 0u;
         internal = (i == 0 || !leaf) ? 1u : 0u; // the root always has a record (a leaf root points at itself)
-        keys[i] = i == 0 ? 0 : (leaf ? 31 : (uint8_t)min(ld & 0x7FFFFFFFu, 30u));
+        if (internal && i != 0) {
+            // leaf brick: all eight children are leaves (their colours are this record's eight words)
+            brick = 1u;
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t child = raw[i * 10u + (uint32_t)c];
+                if (child >= count || !(raw[(uint64_t)child * 10u + 9u] & 0x80000000u)) brick = 0u;
+            }
+        }
+        keys[i] = i == 0 ? 0 : (leaf ? 31 : (brick ? 30 : (uint8_t)min(ld & 0x7FFFFFFFu, 29u)));
         vals[i] = (uint32_t)i;
     }
     const unsigned n = __popc(__ballot_sync(0xFFFFFFFFu, internal != 0u));
+    const unsigned nb = __popc(__ballot_sync(0xFFFFFFFFu, brick != 0u));
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(n_internal, (unsigned long long)n);
+    if ((threadIdx.x & 31) == 0 && nb) atomicAdd(n_internal + 1, (unsigned long long)nb);
 }
 
 __global__ void compact_rank_kernel(const uint32_t* __restrict__ order, uint64_t n_internal, uint32_t* __restrict__ rank) {
@@ -133,7 +145,7 @@ __global__ void compact_emit_kernel(const uint32_t* __restrict__ raw, uint64_t c
 }
 
 cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, uint64_t* n_internal_out,
-                                cudaStream_t stream) {
+                                uint32_t* brick_base_out, cudaStream_t stream) {
     *out = nullptr;
     uint8_t *k_in = nullptr, *k_out = nullptr;
     uint32_t *v_in = nullptr, *v_out = nullptr, *rank = nullptr;
@@ -152,8 +164,8 @@ cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, 
     XN_TRY(cudaMalloc(&v_in, count * 4));
     XN_TRY(cudaMalloc(&v_out, count * 4));
     XN_TRY(cudaMalloc(&rank, count * 4));
-    XN_TRY(cudaMalloc(&d_n, 8));
-    XN_TRY(cudaMemsetAsync(d_n, 0, 8, stream));
+    XN_TRY(cudaMalloc(&d_n, 16));
+    XN_TRY(cudaMemsetAsync(d_n, 0, 16, stream));
     const int threads = 256;
     const unsigned blocks = (unsigned)((count + threads - 1) / threads);
     compact_keys_kernel<<<blocks, threads, 0, stream>>>((const uint32_t*)raw40, count, k_in, v_in, d_n);
@@ -162,9 +174,10 @@ cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, 
     XN_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)count, 0, 5, stream));
     XN_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
     XN_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int64_t)count, 0, 5, stream));
-    unsigned long long n_internal = 0;
-    XN_TRY(cudaMemcpyAsync(&n_internal, d_n, 8, cudaMemcpyDeviceToHost, stream));
+    unsigned long long counts[2] = {0, 0}; // internal nodes, of which leaf bricks
+    XN_TRY(cudaMemcpyAsync(counts, d_n, 16, cudaMemcpyDeviceToHost, stream));
     XN_TRY(cudaStreamSynchronize(stream));
+    const unsigned long long n_internal = counts[0];
     if (n_internal > (1ull << 28)) return done(cudaErrorInvalidValue); // word offsets must fit 31 bits
     XN_TRY(cudaMalloc(&nodes, n_internal * sizeof(CNode)));
     const unsigned iblocks = (unsigned)((n_internal + threads - 1) / threads);
@@ -176,6 +189,7 @@ cudaError_t build_compact_nodes(const void* raw40, uint64_t count, CNode** out, 
 #undef XN_TRY
     *out = nodes;
     *n_internal_out = n_internal;
+    *brick_base_out = (uint32_t)((n_internal - counts[1]) << 3);
     return done(cudaSuccess);
 }
 

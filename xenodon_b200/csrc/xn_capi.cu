@@ -235,8 +235,11 @@ void fill_params(xn_ctx* ctx, int traversal, const float fwd[3], const float up[
     p.cnodes = ctx->cnodes;
     {
         // XN_ESVO_BRICKS=0: the fast-mode ESVO descends into leaf bricks child by child, as the strict mode does
+        // XN_ESVO_BRICKS=1: the fast-mode ESVO integrates leaf bricks in closed form (esvo_leaf_brick;
+        // measured: +4 % on the dense bunny tree, -20 % on the sparse 2048^3 tree, hence an opt-in)
         const char* e = std::getenv("XN_ESVO_BRICKS");
-        p.brick_base = (e && e[0] == '0') ? 0xFFFFFFFFu : ctx->brick_base;
+        const bool on = e && e[0] == '1' && ctx->brick_base != 0xFFFFFFFFu;
+        p.brick_base = on ? ctx->brick_base : 0xFFFFFFFFu;
     }
     p.top_table = ctx->top_table;
     p.top_levels = ctx->top_levels;

@@ -1807,8 +1807,15 @@ __device__ __forceinline__ uint32_t esvo_first_child(float tcenx, float tceny, f
 // ahead.  These are the chords esvo.comp:65-104 walks through (a child's exit time is the next
 // crossing), up to the rounding of t -- which is why the strict mode keeps the loop.  Chords of
 // length zero (a plane crossed outside the stay, or two at once) add colour x 0.
-#ifndef XN_ESVO_BRICKS
-#define XN_ESVO_BRICKS 1
+// Measured (profiles/README.md, round 2 session 4): on the bunny tree, script frame 120, 46 % fewer loop
+// iterations, 19 % fewer warp instructions, 21.2 -> 23.1 lanes per instruction, kernel time -13 %;
+// whole camera path +4 % (1203 -> 1252 Mrays/s).  On the 2048^3 TNG tree -20 %: there few lanes of a
+// warp stand before a brick at the same time, and the 80 instructions of the closed form are paid
+// per warp while the iterations they replace were shared with the other lanes' iterations (taking
+// the closed form only when a ballot finds enough such lanes costs more than it saves: 939).  So
+// this is an opt-in (XN_ESVO_BRICKS=1), like the ray pool.
+#ifndef XN_ESVO_BRICK_MIN_BLOCKS
+#define XN_ESVO_BRICK_MIN_BLOCKS 4
 #endif
 template <bool STRICT>
 __device__ __forceinline__ void esvo_leaf_brick(const CNode* __restrict__ nodes, uint32_t s, uint32_t octant_mask,
@@ -1846,8 +1853,11 @@ __device__ __forceinline__ void esvo_leaf_brick(const CNode* __restrict__ nodes,
 // per ray slot).  Rays are numbered so that 32 consecutive ones are an 8x4 tile and 256 a block of
 // the static launch: a freshly filled warp is as coherent as a static one.  What it buys is
 // measured, not assumed: profiles/README.md (ray pool).
-template <bool STATS, bool STRICT, int LEVELS, bool POOL = false>
-__global__ void __launch_bounds__(BLOCK_THREADS, XN_ESVO_MIN_BLOCKS) esvo_kernel(const __grid_constant__ FrameParams p) {
+// BRICKS: child words at or above p.brick_base are leaf bricks (esvo_leaf_brick); a separate
+// instantiation, so trees without them run the plain loop's code unchanged.
+template <bool STATS, bool STRICT, int LEVELS, bool POOL = false, bool BRICKS = false>
+__global__ void __launch_bounds__(BLOCK_THREADS, BRICKS ? XN_ESVO_BRICK_MIN_BLOCKS : XN_ESVO_MIN_BLOCKS)
+    esvo_kernel(const __grid_constant__ FrameParams p) {
     // [scale][thread] = (parent, bits(t_max)).  Trees this instantiation is launched for are shallower
     // than LEVELS; the index is clamped instead of bounds-tested, so a malformed file (a cycle of
     // child pointers) aliases its own thread's last entry and nothing else.  Shared memory is
@@ -1953,7 +1963,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_ESVO_MIN_BLOCKS) esvo_kernel
                 if (word_is_leaf(s)) {
                     st.read(4); // color
                     acc.add(s, tv_max - t_min);
-                } else if (XN_ESVO_BRICKS && !STATS && !STRICT && s >= p.brick_base) {
+                } else if (BRICKS && s >= p.brick_base) {
                     // eight leaves below: integrated here, then ADVANCE as after a leaf
                     esvo_leaf_brick(nodes, s, octant_mask, tcx, tcy, tcz, tcorx, tcory, tcorz, scale_exp2 * 0.5f, t_min,
                                     tv_max, acc);
@@ -2320,6 +2330,8 @@ static cudaError_t launch_t(int traversal, const FrameParams& p, cudaStream_t st
                 break;
             }
             if (deep) esvo_kernel<STATS, STRICT, 24><<<grid, block, 0, stream>>>(p);
+            else if (!STATS && !STRICT && p.brick_base != 0xFFFFFFFFu)
+                esvo_kernel<false, false, 12, false, true><<<grid, block, 0, stream>>>(p);
             else esvo_kernel<STATS, STRICT, 12><<<grid, block, 0, stream>>>(p);
             break;
         case 3:

@@ -337,6 +337,33 @@ def measure_config(xb, ctx, name, traversal, frame, cams, steps, warmup, tree_si
 # --------------------------------------------------------------------------------------------
 # shared page-locked host frames for the multi-GPU e2e path
 # --------------------------------------------------------------------------------------------
+def _interleave_pages(addr, size):
+    """mbind(MPOL_INTERLEAVE) over the online NUMA nodes for a not-yet-touched mapping; returns what
+    happened as text (the bench line reports it).  XN_SHM_INTERLEAVE=0 leaves the default policy."""
+    if os.environ.get("XN_SHM_INTERLEAVE", "1") == "0":
+        return "default policy (XN_SHM_INTERLEAVE=0)"
+    try:
+        import ctypes
+        ids = []
+        for part in open("/sys/devices/system/node/online").read().strip().split(","):
+            a, _, b = part.partition("-")
+            ids += list(range(int(a), int(b or a) + 1))
+        if len(ids) < 2:
+            return "one NUMA node"
+        mask = 0
+        for i in ids:
+            mask |= 1 << i
+        libc = ctypes.CDLL(None, use_errno=True)
+        words = (max(ids) + 64) // 64
+        nodemask = (ctypes.c_ulong * words)(*[(mask >> (64 * w)) & (2**64 - 1) for w in range(words)])
+        a0 = addr & ~4095
+        r = libc.syscall(237, ctypes.c_void_p(a0), ctypes.c_ulong(size + addr - a0), ctypes.c_int(3), nodemask,
+                         ctypes.c_ulong(64 * words + 1), ctypes.c_uint(0))  # SYS_mbind, MPOL_INTERLEAVE
+        return f"pages interleaved over {len(ids)} NUMA nodes" if r == 0 else f"default policy (mbind errno {ctypes.get_errno()})"
+    except Exception as e:  # not Linux / no sysfs / no syscall: the default policy stays
+        return f"default policy ({type(e).__name__})"
+
+
 class SharedHostFrames:
     """`count` frames of w*h RGBA8 + a flag page in ONE POSIX shared-memory segment, mapped by every
     rank and registered with CUDA (xn_host_register) so that device-to-host copies into it are
@@ -358,6 +385,10 @@ class SharedHostFrames:
                 pass
         self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
         self.base = self.buf.ctypes.data
+        # N GPUs write into this one segment over their own PCIe links: spread its pages over the host's
+        # NUMA nodes before anything touches them (pinning allocates them), so the frame does not land on
+        # the memory controllers -- and cross the socket link -- of the creating rank's node alone
+        self.numa = _interleave_pages(self.base, size) if create else None
         xb.host_register(self.base, size)
         self.xb = xb
         self.flags = self.buf[:n_ranks * count * 4].view(np.uint32).reshape(n_ranks, count)
@@ -616,6 +647,41 @@ def main():
                             "processes (POSIX shm + cudaHostRegister): the frame leaves over N PCIe links; per-rank "
                             "stream-ordered completion flags, no collective or host sync inside the loop")
         e2e_info["nvlink_bytes_per_step"] = 0
+        if rank == 0:
+            e2e_info["host_frame_numa"] = shared.numa
+        if last_frame is not None:
+            last_frame = np.array(last_frame, copy=True)  # the probe below overwrites the segment
+        # what the host side of this path can take: every rank copies a device buffer of its share of
+        # the frame into its part of the shared segment, all ranks at once, then rank 0 alone
+        share = (W * H * 4 // n_gpus) & ~4095
+        dev = torch.empty(share, dtype=torch.uint8, device="cuda")
+        dst = torch.from_numpy(shared.buf[shared.flag_bytes + rank * share:shared.flag_bytes + (rank + 1) * share])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+        def copy_rate(active):
+            barrier()
+            ms = 0.0
+            if active:
+                dst.copy_(dev, non_blocking=True)
+                ev[0].record()
+                for _ in range(10):
+                    dst.copy_(dev, non_blocking=True)
+                ev[1].record()
+                torch.cuda.synchronize()
+                ms = ev[0].elapsed_time(ev[1]) / 10
+            t_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_.item())
+
+        ms_all = copy_rate(True)
+        ms_one = copy_rate(rank == 0)
+        e2e_info["d2h_probe"] = {
+            "bytes_per_rank": share,
+            "all_ranks_at_once_gb_per_s": round(share * n_gpus / (ms_all / 1e3) / 1e9, 1) if ms_all > 0 else None,
+            "one_rank_alone_gb_per_s": round(share / (ms_one / 1e3) / 1e9, 1) if ms_one > 0 else None,
+            "note": "contiguous device -> shared host frame copies, CUDA-event timed, max over ranks",
+        }
+        del dev, dst
     else:
         pinned = [xb.PinnedFrame(W, H), xb.PinnedFrame(W, H)] if rank == 0 else None
         if tile is None:

@@ -3,6 +3,7 @@
 # usage: bash tools/final_sweep.sh <tag>        (under gpurun, one GPU)
 set -x
 TAG=${1:-r02}
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; tail -2 gpurun_out/${TAG}_pytest.log
 # every launch of the default bench (cfg4 headline + per_config): cold-cache, serialised -> compare shares
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 6 --warmup 3 > gpurun_out/${TAG}_launches.log 2>&1
@@ -12,17 +13,17 @@ cap() { # workload traversal kernel-regex name launch-skip
   ncu -i gpurun_out/${TAG}_$4.ncu-rep --page raw --csv > gpurun_out/${TAG}_$4_ncu_raw.csv 2>/dev/null
   # per-instruction execution and lane counts (tools/sass_segments.py reads these)
   ncu -i gpurun_out/${TAG}_$4.ncu-rep --page source --csv --print-source sass > gpurun_out/${TAG}_$4_sass.csv 2>/dev/null
-  # gpurun brings back at most 64 MiB: keep the reports of the two headline kernels only
-  case $4 in dda_cfg4_f120|esvo_f120) ;; *) rm -f gpurun_out/${TAG}_$4.ncu-rep ;; esac
+  # the loops themselves, small enough to commit: instructions executed >= 2 % as often as the hottest one
+  python tools/sass_excerpt.py gpurun_out/${TAG}_$4_sass.csv gpurun_out/${TAG}_$4_sass.txt
+  # gpurun brings back at most 64 MiB: keep the report of the headline kernel only
+  case $4 in dda_cfg4_f120) ;; *) rm -f gpurun_out/${TAG}_$4.ncu-rep ;; esac
 }
 # launch-skip = 3 warm-up launches + step index; step s of 20 renders script frame floor(s * 150 / 20):
 # step 2 = frame 15 (outside, distance 2), step 16 = frame 120 (inside the volume)
-cap cfg4 dda dda_ dda_cfg4_f15 5
 cap cfg4 dda dda_ dda_cfg4_f120 19
 cap cfg3 dda dda_ dda_cfg3_f120 19
 cap cfg1 dda dda_ dda_cfg1 5
 cap cfg2 dda dda_ dda_cfg2 19
-cap cfg2 esvo esvo_kernel esvo_f15 5
 cap cfg2 esvo esvo_kernel esvo_f120 19
 cap cfg4e esvo esvo_kernel esvo_cfg4e_f120 19
 cap cfg2 svo-df svo_df df_f120 19

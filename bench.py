@@ -593,12 +593,12 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
         last_frame = pinned[(steps - 1) & 1].array
-        e2e_info["path"] = "xn_render_download_async: two alternating device targets, copy-out of frame i overlaps frame i+1"
+        e2e_info["path"] = "xn_render_download_async: three device targets in rotation, copy-out of frame i overlaps frames i+1, i+2"
     elif gather == "host":
         # every rank copies its own stripes into the shared page-locked frame (N PCIe links);
         # a stream-ordered flag per rank and slot says "frame seq is complete in this slot"
         ctx.set_target_buffer(None, 0)
-        SLOTS = 2
+        SLOTS = 3
         name = [f"xn_bench_{os.getpid()}_{int(time.time())}" if rank == 0 else None]
         dist.broadcast_object_list(name, src=0)
         if rank == 0:
@@ -633,12 +633,14 @@ def main():
         ctx.sync()
         barrier()
         t0 = time.perf_counter()
+        lag = SLOTS - 1  # the consumer trails the producers by this many frames (frames in flight)
         for i, f in enumerate(sched):
             produce(base + 1 + i, f)
-            if rank == 0 and i >= 1:
-                consume(base + i)  # one frame behind: frame i renders while frame i-1 completes
+            if rank == 0 and i >= lag:
+                consume(base + 1 + i - lag)
         if rank == 0:
-            consume(base + steps)
+            for seq in range(max(base + 1, base + 1 + steps - lag), base + steps + 1):
+                consume(seq)
         ctx.sync()
         barrier()
         e2e_s = time.perf_counter() - t0

@@ -210,10 +210,12 @@ XN_API int xn_download(xn_ctx* ctx, uint32_t* dst, size_t stride_px);
 
 /* Pipelined frame output (replaces the blocking staging copy of HeadlessOutput::download,
  * src/backend/headless/HeadlessOutput.cpp:95-136, for movie rendering): renders into one of
- * two alternating device targets and copies the finished region to host_dst (tight rows,
+ * three device targets used in rotation and copies the finished region to host_dst (tight rows,
  * region w*h pixels; pinned memory from xn_host_alloc makes the copy asynchronous) on a
- * second stream, so the copy of frame i overlaps the traversal of frame i+1.  host_dst is
- * valid after the next xn_sync.  Not combinable with xn_set_target_buffer. */
+ * second stream, so the copy of frame i overlaps the traversal of frames i+1 and i+2.  Copies
+ * complete in call order; host_dst is valid after the next xn_sync (or, for
+ * xn_render_download_to, once its xn_signal_after_copy flag shows).  Not combinable with
+ * xn_set_target_buffer. */
 XN_API int xn_render_download_async(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
                                     const float translation[3], uint32_t* host_dst);
 XN_API int xn_host_alloc(size_t bytes, void** out); /* page-locked host memory */

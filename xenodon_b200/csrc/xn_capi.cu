@@ -86,10 +86,14 @@ struct xn_ctx {
 
     // pipelined frame output: two alternating targets + a copy stream
     cudaStream_t copy_stream = nullptr;
-    uint32_t* pipe_target[2] = {nullptr, nullptr};
+    // pipelined frame output: PIPE_DEPTH device targets in rotation, so the traversal may run up to
+    // PIPE_DEPTH - 1 frames ahead of the copy-out (two balanced stages with only two buffers stall on
+    // each other's jitter: 8 GPUs feeding one host at its ingest limit, profiles/README.md)
+    static constexpr int PIPE_DEPTH = 3;
+    uint32_t* pipe_target[PIPE_DEPTH] = {};
     uint64_t pipe_target_px = 0;
-    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    bool copy_in_flight[2] = {false, false};
+    cudaEvent_t ev_rendered[PIPE_DEPTH] = {}, ev_copied[PIPE_DEPTH] = {};
+    bool copy_in_flight[PIPE_DEPTH] = {};
     bool frame_read_in_flight = false;
     int pipe_next = 0;
     double last_ms = 0;
@@ -564,7 +568,7 @@ int xn_ctx_create(int cuda_device, xn_ctx** out) {
         XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_gather, cudaEventDisableTiming));
         XN_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         XN_CUDA(cudaMalloc(&ctx->ray_pool, 256));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < xn_ctx::PIPE_DEPTH; ++i) {
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_rendered[i], cudaEventDisableTiming));
             XN_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
         }
@@ -578,9 +582,10 @@ int xn_ctx_destroy(xn_ctx* ctx) {
         DeviceGuard g(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-        for (int i = 0; i < 2; ++i) {
-            if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
+        for (int i = 0; i < 2; ++i)
             if (ctx->ev_mark[i]) cudaEventDestroy(ctx->ev_mark[i]);
+        for (int i = 0; i < xn_ctx::PIPE_DEPTH; ++i) {
+            if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
             if (ctx->ev_rendered[i]) cudaEventDestroy(ctx->ev_rendered[i]);
             if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         }
@@ -1048,18 +1053,17 @@ void render_download(xn_ctx* ctx, int traversal, const float forward[3], const f
     if (px > ctx->pipe_target_px) {
         XN_CUDA(cudaStreamSynchronize(ctx->stream));
         XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < xn_ctx::PIPE_DEPTH; ++i) {
             if (ctx->pipe_target[i]) cudaFree(ctx->pipe_target[i]);
             ctx->pipe_target[i] = nullptr;
             ctx->copy_in_flight[i] = false;
         }
         ctx->pipe_target_px = 0;
-        XN_CUDA(cudaMalloc(&ctx->pipe_target[0], px * 4));
-        XN_CUDA(cudaMalloc(&ctx->pipe_target[1], px * 4));
+        for (int i = 0; i < xn_ctx::PIPE_DEPTH; ++i) XN_CUDA(cudaMalloc(&ctx->pipe_target[i], px * 4));
         ctx->pipe_target_px = px;
     }
     const int b = ctx->pipe_next;
-    ctx->pipe_next ^= 1;
+    ctx->pipe_next = (b + 1) % xn_ctx::PIPE_DEPTH;
     // the traversal may only overwrite target b once its previous copy-out has finished
     if (ctx->copy_in_flight[b]) XN_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
     p.target = ctx->pipe_target[b];
@@ -1202,9 +1206,11 @@ int xn_sync(xn_ctx* ctx, double* kernel_ms) {
         check_ctx(ctx);
         DeviceGuard g(ctx->device);
         XN_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->copy_in_flight[0] || ctx->copy_in_flight[1] || ctx->frame_read_in_flight) {
+        bool copying = ctx->frame_read_in_flight;
+        for (bool f : ctx->copy_in_flight) copying = copying || f;
+        if (copying) {
             XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-            ctx->copy_in_flight[0] = ctx->copy_in_flight[1] = false;
+            for (bool& f : ctx->copy_in_flight) f = false;
             ctx->frame_read_in_flight = false;
         }
         if (ctx->timing_pending) {
@@ -1427,7 +1433,7 @@ int xn_copy_sync(xn_ctx* ctx) {
         check_ctx(ctx);
         DeviceGuard g(ctx->device);
         XN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-        ctx->copy_in_flight[0] = ctx->copy_in_flight[1] = false;
+        for (bool& f : ctx->copy_in_flight) f = false;
         ctx->frame_read_in_flight = false;
     });
 }

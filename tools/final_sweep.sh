@@ -30,6 +30,11 @@ cap cfg2 svo-df svo_df df_f120 19
 cap cfg2 svo-rope svo_rope rope_f120 19
 cap cfg3r svo-rope svo_rope rope_cfg3r_f120 19
 cap cfg2 svo-naive svo_naive_kernel naive_f120 19
+# memory and shared-memory race checks of the GPU suites (small inputs; the full-size tests are left out)
+compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_ingest.py \
+  tests/test_gpu_convert.py tests/test_gpu_cli.py -m gpu -q -x > gpurun_out/${TAG}_memcheck.log 2>&1; tail -3 gpurun_out/${TAG}_memcheck.log
+compute-sanitizer --tool racecheck --error-exitcode 1 python -m pytest tests/test_gpu_parity.py -m gpu -q -x \
+  -k "svo_matches and (esvo or svo-df) and blobby" > gpurun_out/${TAG}_racecheck.log 2>&1; tail -3 gpurun_out/${TAG}_racecheck.log
 # un-profiled bench lines: the driver's command, longer runs of every workload, the reference arm
 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err
 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err

@@ -821,6 +821,19 @@ struct TexUniform<true> {
 // On return s is the first crossing not below T, kf has grown by the crossings taken and t_last is
 // the latest of them.  (Prototype checked against the sequential additions on 3 10^5 random
 // (s, d, T) including tie-prone d: tools/jump_proto.py.)
+//
+// XN_SKIP_ONE_BINADE = 1 caps T at the top of every axis' current binade (dda_binade_top), so that a
+// jump never continues in the next binade: a lane crosses a power of two in about 2 % of its jumps
+// at large t, but a warp repeats the loop body when any of its lanes has to (42 % of the warps, ncu
+// r02g).  Measured slower (cfg4 1818 -> 1750, cfg1 9313 -> 7786): near the start of a ray binades
+// are a few steps long and a promise spans several, and a lane cut short asks for another jump round
+// (130 instructions for the warp) where the repeated loop body cost 40.  Off.
+#ifndef XN_SKIP_ONE_BINADE
+#define XN_SKIP_ONE_BINADE 0
+#endif
+__device__ __forceinline__ float dda_binade_top(float s) { // 2^(e+1) for s in [2^e, 2^(e+1))
+    return __uint_as_float((__float_as_uint(s) & 0x7F800000u) + 0x00800000u);
+}
 __device__ __forceinline__ void dda_axis_jump(float& s, const float d, const float T, float& t_last, float& kf) {
     while (s < T) {
         const float s1 = s + d, q = s1 - s; // one real addition: the next crossing, and the increment
@@ -830,7 +843,7 @@ __device__ __forceinline__ void dda_axis_jump(float& s, const float d, const flo
         if (s1 < top && (fabsf(d - q) != half_u || (sb & 1u) == 0u)) {
             // s, s + q, ... below hi = min(T, 2^(e+1)) are all crossings taken; the one after the
             // last of them is a real addition again (it may leave the binade, or pass T)
-            const float hi = fminf(T, top);
+            const float hi = XN_SKIP_ONE_BINADE ? T : fminf(T, top);
             float jf = floorf(__fdividef(hi - s, q) * 0.99999f);
             float sj = __fmaf_rn(jf, q, s);
             while (sj + q < hi) {
@@ -1004,7 +1017,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
             if (hop != 0 && __any_sync(am, !(t < t_look))) XN_SKIP_LOOKUP(PEND)                      \
             /* every step that ends before T lands on a promised texel and leaves a whole trip before */ \
             /* the end of the ray: take them all at once, each lane its own T                        */ \
-            const float T = fminf(XN_SKIP_FULL ? t_safe : t_safe - td45, t_lim4);                    \
+            float T = fminf(XN_SKIP_FULL ? t_safe : t_safe - td45, t_lim4);                          \
+            if (XN_SKIP_ONE_BINADE)                                                                 \
+                T = fminf(T, fminf(dda_binade_top(sdx), fminf(dda_binade_top(sdy), dda_binade_top(sdz)))); \
             /* a lane jumps if at least one step ends before T.  If the texel pending its segment was */ \
             /* fetched (the trip before this fetched), the first of those steps closes it: its       */ \
             /* length goes to plen, which the next trip adds when it consumes that texel -- so a     */ \

@@ -809,9 +809,10 @@ def main():
                 host_grid = np.zeros((1, 1, 1, 4), np.uint8)  # unused by the octree traversals
                 if tree is None:
                     raise RuntimeError("node array of this volume is not brought back to the host")
-            k = max(2, min(steps, 6))
+            # about 10 s of CPU work: 12 frames spread over the script x 16 bands of 8 rows
+            k = max(2, min(steps, 12))
             sub = [cam_tuple(cams, f) for f in frame_schedule(len(cams), k)]
-            bands = oracle_sample_rows(H, bands=8, rows_per_band=4 if W * H > 4_000_000 else 8)
+            bands = oracle_sample_rows(H, bands=16, rows_per_band=8)
             mr, info = run_oracle_frames(traversal, (W, H), sub[:1] + sub, host_grid, tree, bands=bands)
             result["cpu_baseline"] = {"value": round(mr, 3), "unit": "Mrays/s", "cores": info["cores"],
                                       "kind": info["kind"], "sample": info["sample"],
@@ -914,8 +915,7 @@ def run_reference_arm(args, workload, wl, traversal, frame, cams, n_gpus, weak):
     sched = frame_schedule(len(cams), steps)
     n = max(1, min(steps, 24))
     pick = [sched[(i * len(sched)) // n] for i in range(n)]
-    rows_per_band = 8 if W * H <= 4_000_000 else 4
-    bands = oracle_sample_rows(H, bands=8, rows_per_band=rows_per_band)
+    bands = oracle_sample_rows(H, bands=8, rows_per_band=16)
     cam_list = [cam_tuple(cams, f) for f in pick]
     warm = min(max(warmup, 0), 1)
     t1 = time.perf_counter()

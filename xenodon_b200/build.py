@@ -119,6 +119,7 @@ def build_variant(name: str, defs: str) -> str:
     others += [os.path.join(OBJ, src.replace("/", "_") + ".o") for src in CPP_SOURCES]
     out = os.path.join(vdir, f"libxenodon_b200_{name}.so")
     _run([nvcc, "-ccbin", gxx, *ARCH, "-shared", "-o", out, obj, *others, "-lz", "-Xlinker", "--no-undefined"])
+    os.remove(obj)  # 4 MB each, and build/ travels with every gpurun snapshot
     return out
 
 

@@ -337,87 +337,6 @@ def measure_config(xb, ctx, name, traversal, frame, cams, steps, warmup, tree_si
 # --------------------------------------------------------------------------------------------
 # shared page-locked host frames for the multi-GPU e2e path
 # --------------------------------------------------------------------------------------------
-def _interleave_pages(addr, size):
-    """mbind(MPOL_INTERLEAVE) over the online NUMA nodes for a not-yet-touched mapping; returns what
-    happened as text (the bench line reports it).  XN_SHM_INTERLEAVE=0 leaves the default policy."""
-    if os.environ.get("XN_SHM_INTERLEAVE", "1") == "0":
-        return "default policy (XN_SHM_INTERLEAVE=0)"
-    try:
-        import ctypes
-        ids = []
-        for part in open("/sys/devices/system/node/online").read().strip().split(","):
-            a, _, b = part.partition("-")
-            ids += list(range(int(a), int(b or a) + 1))
-        if len(ids) < 2:
-            return "one NUMA node"
-        mask = 0
-        for i in ids:
-            mask |= 1 << i
-        libc = ctypes.CDLL(None, use_errno=True)
-        words = (max(ids) + 64) // 64
-        nodemask = (ctypes.c_ulong * words)(*[(mask >> (64 * w)) & (2**64 - 1) for w in range(words)])
-        a0 = addr & ~4095
-        r = libc.syscall(237, ctypes.c_void_p(a0), ctypes.c_ulong(size + addr - a0), ctypes.c_int(3), nodemask,
-                         ctypes.c_ulong(64 * words + 1), ctypes.c_uint(0))  # SYS_mbind, MPOL_INTERLEAVE
-        return f"pages interleaved over {len(ids)} NUMA nodes" if r == 0 else f"default policy (mbind errno {ctypes.get_errno()})"
-    except Exception as e:  # not Linux / no sysfs / no syscall: the default policy stays
-        return f"default policy ({type(e).__name__})"
-
-
-class SharedHostFrames:
-    """`count` frames of w*h RGBA8 + a flag page in ONE POSIX shared-memory segment, mapped by every
-    rank and registered with CUDA (xn_host_register) so that device-to-host copies into it are
-    asynchronous.  flags[rank, slot] = sequence number of the last frame rank copied into slot."""
-
-    def __init__(self, xb, name, w, h, count, n_ranks, create):
-        from multiprocessing import shared_memory
-        self.frame_bytes = w * h * 4
-        self.flag_bytes = 4096
-        size = self.flag_bytes + count * self.frame_bytes
-        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size)
-        if not create:
-            # only the creating rank owns the segment: keep this process's resource tracker from
-            # unlinking (and warning about) a segment it merely attached to
-            try:
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(self.shm._name, "shared_memory")
-            except Exception:
-                pass
-        self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
-        self.base = self.buf.ctypes.data
-        # N GPUs write into this one segment over their own PCIe links: spread its pages over the host's
-        # NUMA nodes before anything touches them (pinning allocates them), so the frame does not land on
-        # the memory controllers -- and cross the socket link -- of the creating rank's node alone
-        self.numa = _interleave_pages(self.base, size) if create else None
-        xb.host_register(self.base, size)
-        self.xb = xb
-        self.flags = self.buf[:n_ranks * count * 4].view(np.uint32).reshape(n_ranks, count)
-        self.frames = [self.buf[self.flag_bytes + i * self.frame_bytes:self.flag_bytes + (i + 1) * self.frame_bytes]
-                       .reshape(h, w, 4) for i in range(count)]
-        self.create = create
-        if create:
-            self.flags[...] = 0
-
-    def frame_ptr(self, i):
-        return self.base + self.flag_bytes + i * self.frame_bytes
-
-    def flag_ptr(self, rank, slot):
-        return self.base + (rank * self.flags.shape[1] + slot) * 4
-
-    def close(self):
-        try:
-            self.xb.host_unregister(self.base)
-        except Exception:
-            pass
-        self.flags = self.frames = self.buf = None
-        try:
-            self.shm.close()
-            if self.create:
-                self.shm.unlink()
-        except Exception:
-            pass
-
-
 # --------------------------------------------------------------------------------------------
 def main():
     # keep stdout for the ONE JSON line: libraries (NCCL's version banner, torchrun notices)
@@ -466,6 +385,7 @@ def main():
     import torch.distributed as dist
 
     import xenodon_b200 as xb
+    from xenodon_b200 import distributed as xd
 
     torch.cuda.set_device(local_rank)
     if n_gpus > 1:
@@ -602,27 +522,23 @@ def main():
         name = [f"xn_bench_{os.getpid()}_{int(time.time())}" if rank == 0 else None]
         dist.broadcast_object_list(name, src=0)
         if rank == 0:
-            shared = SharedHostFrames(xb, name[0], W, H, SLOTS, n_gpus, create=True)
+            shared = xd.SharedHostFrames(name[0], W, H, SLOTS, n_gpus, create=True, register=xb.host_register,
+                                           unregister=xb.host_unregister)
         dist.barrier()
         if rank != 0:
-            shared = SharedHostFrames(xb, name[0], W, H, SLOTS, n_gpus, create=False)
+            shared = xd.SharedHostFrames(name[0], W, H, SLOTS, n_gpus, create=False, register=xb.host_register,
+                                           unregister=xb.host_unregister)
         dist.barrier()
-        ack = shared.buf[2048:2052].view(np.uint32)  # frames rank 0 has seen complete (consumer side)
+        ring = xd.HostFrameRing(shared, rank)
 
         def produce(seq, f):
-            slot = seq % SLOTS
-            # the consumer must have released this slot (frame seq - SLOTS) before it is overwritten
-            while seq > SLOTS and int(ack[0]) < seq - SLOTS:
-                pass
+            slot = ring.acquire(seq)  # the consumer has released the frame this slot held
             ctx.render_download_to(traversal, cam_tuple(cams, f), shared.frame_ptr(slot), W)
             ctx.signal_after_copy(shared.flag_ptr(rank, slot), seq)
 
         def consume(seq):
-            slot = seq % SLOTS
-            fl = shared.flags[:, slot]
-            while int(fl.min()) < seq:
-                pass
-            ack[0] = seq  # a consumer (PNG writer, display) would use shared.frames[slot] here
+            ring.wait_complete(seq)  # a consumer (PNG writer, display) would use shared.frames[slot] here
+            ring.release(seq)
 
         base = 0
         for j, f in enumerate(warm_sched[:3]):

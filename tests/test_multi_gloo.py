@@ -58,3 +58,22 @@ def test_two_rank_gloo_gather_equals_single_rank_frame(tmp_path, xo):
     res = json.loads(out.read_text())
     assert res["world"] == 2 and res["equal"] is True
     assert res["stats"]["total_rays"] == 100 * 70 and res["stats"]["max_render_time"] == 2.0
+
+
+def test_shared_host_frame_ring(tmp_path):
+    """The multi-GPU e2e protocol on CPU: two gloo ranks deliver their stripes into one shared host
+    frame ring (three slots), rank 0 consumes two frames behind; every frame must be complete when
+    it is seen and intact until it is released."""
+    out = tmp_path / "ring.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29633", os.path.join(ROOT, "tests", "_ring_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(out.read_text())
+    assert res["world"] == 2 and res["bad"] == [] and res["released"] == res["frames"]
+
+
+def test_host_frame_ring_rejects_too_many_flags():
+    from xenodon_b200 import distributed as xd
+    with pytest.raises(ValueError):
+        xd.SharedHostFrames("xn_never_created", 8, 8, 64, 16, create=True)

@@ -12,6 +12,9 @@ in two flavours:
 from __future__ import annotations
 
 import math
+import os
+
+import numpy as np
 
 STRIPE_ROWS = 16  # = BLOCK_H of the traversal kernels
 
@@ -90,3 +93,135 @@ def gather_stripes(dist, local_rows, width: int, height: int, rank: int, world: 
         return frame
     dist.send(local_rows.contiguous(), dst=0)
     return None
+
+
+# --------------------------------------------------------------------------------------------
+# One host frame shared by N processes (one per GPU): every rank delivers its own stripes over its
+# own PCIe link (xn_render_download_to) and flags completion in stream order
+# (xn_signal_after_copy); the consumer polls the flags.  Replaces the host composite of
+# HeadlessDisplay::save (reference src/backend/headless/HeadlessDisplay.cpp:59-76) without a
+# gathering device.  Nothing here touches CUDA: page-locking is an injected callable, so the
+# protocol runs under gloo on CPU (tests/test_multi_gloo.py).
+# --------------------------------------------------------------------------------------------
+def interleave_pages(addr: int, size: int) -> str:
+    """mbind(MPOL_INTERLEAVE) over the online NUMA nodes for a not-yet-touched mapping, so that N
+    GPUs writing one segment do not all land on the creating rank's memory controllers; returns
+    what happened as text.  XN_SHM_INTERLEAVE=0 leaves the default policy."""
+    if os.environ.get("XN_SHM_INTERLEAVE", "1") == "0":
+        return "default policy (XN_SHM_INTERLEAVE=0)"
+    try:
+        import ctypes
+        ids = []
+        for part in open("/sys/devices/system/node/online").read().strip().split(","):
+            a, _, b = part.partition("-")
+            ids += list(range(int(a), int(b or a) + 1))
+        if len(ids) < 2:
+            return "one NUMA node"
+        mask = 0
+        for i in ids:
+            mask |= 1 << i
+        libc = ctypes.CDLL(None, use_errno=True)
+        words = (max(ids) + 64) // 64
+        nodemask = (ctypes.c_ulong * words)(*[(mask >> (64 * w)) & (2**64 - 1) for w in range(words)])
+        a0 = addr & ~4095
+        r = libc.syscall(237, ctypes.c_void_p(a0), ctypes.c_ulong(size + addr - a0), ctypes.c_int(3), nodemask,
+                         ctypes.c_ulong(64 * words + 1), ctypes.c_uint(0))  # SYS_mbind, MPOL_INTERLEAVE
+        return f"pages interleaved over {len(ids)} NUMA nodes" if r == 0 else f"default policy (mbind errno {ctypes.get_errno()})"
+    except Exception as e:  # not Linux / no sysfs / no syscall: the default policy stays
+        return f"default policy ({type(e).__name__})"
+
+
+class SharedHostFrames:
+    """`count` frames of w*h RGBA8 behind one flag page, in ONE POSIX shared-memory segment mapped by
+    every rank.  `register(addr, bytes)` page-locks the mapping for CUDA (xn_host_register) so that
+    device-to-host copies into it are asynchronous; None on a CPU-only run.
+    flags[rank, slot] = sequence number of the last frame `rank` delivered into `slot`;
+    ack[0] = last frame the consumer has released."""
+
+    FLAG_BYTES = 4096
+    ACK_OFFSET = 2048  # ranks * count * 4 bytes of flags must stay below this
+
+    def __init__(self, name, w, h, count, n_ranks, create, register=None, unregister=None):
+        from multiprocessing import shared_memory
+        if n_ranks * count * 4 > self.ACK_OFFSET:
+            raise ValueError("too many ranks x slots for the flag page")
+        self.frame_bytes = w * h * 4
+        self.flag_bytes = self.FLAG_BYTES
+        self.count = count
+        size = self.flag_bytes + count * self.frame_bytes
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size)
+        if not create:
+            # only the creating rank owns the segment: keep this process's resource tracker from
+            # unlinking (and warning about) a segment it merely attached to
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.buf = np.frombuffer(self.shm.buf, dtype=np.uint8)
+        self.base = self.buf.ctypes.data
+        # before anything touches the pages (pinning allocates them)
+        self.numa = interleave_pages(self.base, size) if create else None
+        self._unregister = unregister
+        if register is not None:
+            register(self.base, size)
+        self.flags = self.buf[:n_ranks * count * 4].view(np.uint32).reshape(n_ranks, count)
+        self.ack = self.buf[self.ACK_OFFSET:self.ACK_OFFSET + 4].view(np.uint32)
+        self.frames = [self.buf[self.flag_bytes + i * self.frame_bytes:self.flag_bytes + (i + 1) * self.frame_bytes]
+                       .reshape(h, w, 4) for i in range(count)]
+        self.create = create
+        if create:
+            self.flags[...] = 0
+            self.ack[0] = 0
+
+    def frame_ptr(self, i):
+        return self.base + self.flag_bytes + i * self.frame_bytes
+
+    def flag_ptr(self, rank, slot):
+        return self.base + (rank * self.flags.shape[1] + slot) * 4
+
+    def close(self):
+        try:
+            if self._unregister is not None:
+                self._unregister(self.base)
+        except Exception:
+            pass
+        self.flags = self.ack = self.frames = self.buf = None
+        try:
+            self.shm.close()
+            if self.create:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+class HostFrameRing:
+    """Producer / consumer order over SharedHostFrames.  Frames are numbered 1, 2, ...; frame seq
+    lives in slot seq % count.  A producer may fill a slot only after the consumer has released the
+    frame that slot held before (seq - count); the consumer sees frame seq complete when every
+    rank's flag for its slot has reached seq.  Busy-waiting on purpose: the waits are a fraction of a
+    frame time and the flags are written by CUDA host callbacks, not by Python."""
+
+    def __init__(self, shared: SharedHostFrames, rank: int):
+        self.s, self.rank = shared, rank
+
+    def slot(self, seq: int) -> int:
+        return seq % self.s.count
+
+    def acquire(self, seq: int) -> int:
+        """Producer: wait until slot(seq) may be overwritten; returns the slot."""
+        need = seq - self.s.count
+        while need > 0 and int(self.s.ack[0]) < need:
+            pass
+        return self.slot(seq)
+
+    def wait_complete(self, seq: int) -> int:
+        """Consumer: wait until every rank has delivered frame seq; returns the slot."""
+        fl = self.s.flags[:, self.slot(seq)]
+        while int(fl.min()) < seq:
+            pass
+        return self.slot(seq)
+
+    def release(self, seq: int):
+        """Consumer: frame seq (and every earlier one) is no longer needed."""
+        self.s.ack[0] = seq

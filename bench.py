@@ -306,6 +306,31 @@ def roofline_block(workload, traversal, kernel_name, alg_bytes, alg_steps, n_sta
     return block
 
 
+def compulsory_traffic(xb, ctx, traversal, cams, sched, kernel_ms):
+    """SURVEY 8(d)'s sector-granular lower bound for the DDA, on the schedule's 4/5-point frame (script
+    frame 120 of 150 = the frame the committed ncu capture holds): distinct voxels and distinct 32-byte
+    sectors (of the x-major linear volume) one frame fetches -- as the shader requests them, and as the
+    skip table leaves them -- from the instrumented pass (untimed)."""
+    if traversal != "dda" or ctx.grid_layout()[0] != xb.LAYOUT_TEXTURE:
+        return None
+    try:
+        i = min(len(sched) - 1, (4 * len(sched)) // 5)
+        cam = cam_tuple(cams, sched[i])
+        out = {"script_frame": int(sched[i]), "kernel_ms_of_that_frame": round(float(kernel_ms[i]), 4)}
+        for key, skip in (("as_requested_by_the_shader", False), ("fetched_with_the_skip_table", True)):
+            if skip and os.environ.get("XN_DDA_SKIP", "1") == "0":
+                continue
+            vox, sec = ctx.touch_pass(cam, use_skip_table=skip)
+            out[key] = {"distinct_voxels": vox, "distinct_sectors_32B": sec, "bytes": sec * 32,
+                        "gb_per_s_at_that_frame": round(sec * 32 / (float(kernel_ms[i]) / 1e3) / 1e9, 1)}
+        out["note"] = ("a frame cannot move fewer bytes from HBM than the distinct sectors it fetches (x 32 B; "
+                       "linear-layout sectors, the texture residency's tiles group voxels differently); compare "
+                       "with roofline.traffic (ncu DRAM bytes of the same frame)")
+        return out
+    except Exception as e:  # an explanatory figure must not take the bench line down
+        return {"error": str(e)}
+
+
 def kernel_name_for(xb, ctx, traversal):
     name = KERNEL_NAMES[traversal]
     if traversal == "dda" and ctx.grid_layout()[0] == xb.LAYOUT_TEXTURE:
@@ -325,12 +350,16 @@ def measure_config(xb, ctx, name, traversal, frame, cams, steps, warmup, tree_si
     alg_b, alg_s, n_stat = algorithmic_bytes(ctx, traversal, cams, sched, W * H)
     value = W * H * len(sched) / (ms / 1e3) / 1e6
     kname = kernel_name_for(xb, ctx, traversal)
+    roof = roofline_block(name, traversal, kname, alg_b, alg_s, n_stat, float(np.mean(kms)), 1)
+    lb = compulsory_traffic(xb, ctx, traversal, cams, sched, kms)
+    if lb:
+        roof["sector_lower_bound"] = lb
     return {
         "workload": f"{name}: {WORKLOADS[name]['desc']}" if traversal == WORKLOADS[name]["traversal"]
         else f"{name} volume, --shader {traversal}",
         "traversal": traversal, "value": round(value, 2), "unit": "Mrays/s",
         "ms_per_step": round(ms / len(sched), 5), "frames_per_s": round(len(sched) / (ms / 1e3), 2), "steps": len(sched),
-        "roofline": roofline_block(name, traversal, kname, alg_b, alg_s, n_stat, float(np.mean(kms)), 1),
+        "roofline": roof,
     }
 
 
@@ -715,6 +744,10 @@ def main():
     }
     if single:
         result["single_gpu_same_workload"] = single
+    if n_gpus == 1 and extras:
+        lb = compulsory_traffic(xb, ctx, traversal, cams, sched, kernel_ms)
+        if lb:
+            result["roofline"]["sector_lower_bound"] = lb
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample of the same workload ----
     if extras:

@@ -250,6 +250,13 @@ XN_API int xn_launch_count(const xn_ctx* ctx, uint64_t* count);
 XN_API int xn_render_stats_pass(xn_ctx* ctx, int traversal, const float forward[3], const float up[3],
                                 const float translation[3], uint32_t* steps_out, uint64_t* bytes_out,
                                 uint64_t totals_out[2]);
+/* Which voxels a DDA frame fetches (not timed; texture residency only): counts_out[0] = distinct
+ * voxels fetched by the frame's rays, counts_out[1] = distinct 32-byte sectors of the x-major linear
+ * volume (8 consecutive voxels) holding them -- the compulsory traffic of the frame, SURVEY 8(d)'s
+ * sector-granular lower bound, to set beside the measured DRAM bytes.  use_skip_table 0 = every step
+ * of dda.comp:41-50 fetches (what the shader requests); 1 = the fetches the skip table leaves. */
+XN_API int xn_render_touch_pass(xn_ctx* ctx, const float forward[3], const float up[3], const float translation[3],
+                                int use_skip_table, uint64_t counts_out[2]);
 
 /* ---- multi-device frame assembly: HeadlessDisplay::save's composite,
  *      src/backend/headless/HeadlessDisplay.cpp:59-76 ----

@@ -486,3 +486,44 @@ def test_esvo_ray_pool_matches_oracle(xb, xo, cam, monkeypatch):
         ctxs[0].frame_buffer_close(ptr)
         for c in ctxs:
             c.close()
+
+
+def test_touch_pass_counts_the_voxels_a_frame_fetches(xb, xo):
+    """xn_render_touch_pass: distinct voxels / 32-byte linear sectors fetched by a DDA frame.  Without
+    the skip table every step of dda.comp:41-50 fetches, so a frame cannot touch more voxels than it
+    takes steps, nor more than the volume holds; a dense frame from outside sees (nearly) the whole
+    volume; eight voxels share a sector; the skip table only removes fetches; counts are reproducible
+    and an all-miss camera touches nothing."""
+    rng = np.random.default_rng(3)
+    g = blobby_grid(rng, 64, 40, 48)
+    ctx = xb.Context(0)
+    try:
+        ctx.set_grid_layout(xb.LAYOUT_TEXTURE)
+        ctx.upload_grid(xb.Grid(g))
+        ctx.set_target((0, 0, 320, 180))
+        ctx.set_params((1, 1, 1), None, 1.0)
+        cam = CAMERAS["orbit"]
+        steps = int(ctx.stats_pass("dda", cam, per_ray=False)[2][0])
+        vox, sec = ctx.touch_pass(cam, use_skip_table=False)
+        assert (vox, sec) == ctx.touch_pass(cam, use_skip_table=False)
+        n = 64 * 40 * 48
+        assert 0 < vox <= min(steps, n) and vox > 0.8 * n  # dense rays through 122 880 voxels: all but surface slivers
+        assert (vox + 7) // 8 <= sec <= min(vox, n // 8)
+        vox_s, sec_s = ctx.touch_pass(cam, use_skip_table=True)
+        assert 0 < vox_s <= vox and sec_s <= sec
+        # a camera looking away from the volume fetches nothing
+        away = ((0.0, 0.0, -1.0), (0.0, 1.0, 0.0), (0.5, 0.5, -3.0))
+        assert ctx.touch_pass(away, use_skip_table=False) == (0, 0)
+    finally:
+        ctx.close()
+    # the linear residency is not instrumented: a clear error, not a wrong number
+    ctx = xb.Context(0)
+    try:
+        ctx.set_grid_layout(xb.LAYOUT_LINEAR)
+        ctx.upload_grid(xb.Grid(g))
+        ctx.set_target((0, 0, 64, 36))
+        ctx.set_params((1, 1, 1), None, 1.0)
+        with pytest.raises(xb.XenodonError):
+            ctx.touch_pass(CAMERAS["orbit"])
+    finally:
+        ctx.close()

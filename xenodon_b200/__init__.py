@@ -118,6 +118,8 @@ _PROTOTYPES = {
     "xn_render_stats_pass": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
                                        C.POINTER(C.c_float * 3), C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_uint64 * 2)]),
+    "xn_render_touch_pass": (C.c_int, [C.c_void_p, C.POINTER(C.c_float * 3), C.POINTER(C.c_float * 3),
+                                       C.POINTER(C.c_float * 3), C.c_int, C.POINTER(C.c_uint64 * 2)]),
     "xn_frame_gather": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.POINTER(Rect)]),
     "xn_frame_buffer_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_void_p]),
     "xn_frame_buffer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -481,6 +483,15 @@ class Context:
                                           steps.ctypes.data if per_ray else None,
                                           nbytes.ctypes.data if per_ray else None, C.byref(tot)))
         return steps, nbytes, (tot[0], tot[1])
+
+    def touch_pass(self, camera, use_skip_table: bool = True):
+        """Distinct voxels and distinct 32-byte linear-layout sectors a DDA frame fetches (texture
+        residency): the frame's compulsory traffic.  use_skip_table False = every step fetches."""
+        f, u, p = _f3(camera[0]), _f3(camera[1]), _f3(camera[2])
+        out = (C.c_uint64 * 2)()
+        _check(lib().xn_render_touch_pass(self._h, C.byref(f), C.byref(u), C.byref(p), 1 if use_skip_table else 0,
+                                          C.byref(out)))
+        return int(out[0]), int(out[1])
 
     # frame buffers shared between processes (one process per GPU)
     def frame_buffer_create(self, w: int, h: int):

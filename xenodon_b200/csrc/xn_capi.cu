@@ -1294,6 +1294,51 @@ int xn_render_stats_pass(xn_ctx* ctx, int traversal, const float forward[3], con
     });
 }
 
+int xn_render_touch_pass(xn_ctx* ctx, const float forward[3], const float up[3], const float translation[3],
+                         int use_skip_table, uint64_t counts_out[2]) {
+    return guarded([&] {
+        check_ctx(ctx);
+        if (!counts_out) throw xn::Error(XN_ERR_INVALID, "null argument");
+        counts_out[0] = counts_out[1] = 0;
+        xn::FrameParams p;
+        fill_params(ctx, XN_DDA, forward, up, translation, p);
+        if (p.tex_unorm == 0ull)
+            throw xn::Error(XN_ERR_INVALID, "the touch pass instruments the texture residency (xn_set_grid_layout)");
+        if (!use_skip_table) p.skip_table = nullptr; // every step fetches, as dda.comp:45 does
+        DeviceGuard g(ctx->device);
+        const uint64_t n = (uint64_t)p.out_w * p.out_h;
+        if (n == 0) return;
+        const uint64_t voxels = (uint64_t)p.nx * p.ny * p.nz, words = (voxels + 31) / 32;
+        uint32_t *d_bits = nullptr, *d_target = nullptr;
+        unsigned long long* d_cnt = nullptr;
+        try {
+            XN_CUDA(cudaMalloc(&d_bits, words * 4));
+            XN_CUDA(cudaMalloc(&d_target, n * 4)); // a previous xn_render's image stays untouched
+            XN_CUDA(cudaMalloc(&d_cnt, 16));
+            XN_CUDA(cudaMemsetAsync(d_bits, 0, words * 4, ctx->stream));
+            XN_CUDA(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+            p.touch_bits = d_bits;
+            p.target = d_target;
+            p.target_stride = p.out_w;
+            XN_CUDA(xn::launch_traversal(XN_DDA, p, true, ctx->strict, ctx->stream));
+            XN_CUDA(xn::launch_touch_count(d_bits, words, d_cnt, ctx->stream));
+            unsigned long long h[2] = {0, 0};
+            XN_CUDA(cudaMemcpyAsync(h, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            XN_CUDA(cudaStreamSynchronize(ctx->stream));
+            counts_out[0] = h[0];
+            counts_out[1] = h[1];
+        } catch (...) {
+            cudaFree(d_bits);
+            cudaFree(d_target);
+            cudaFree(d_cnt);
+            throw;
+        }
+        cudaFree(d_bits);
+        cudaFree(d_target);
+        cudaFree(d_cnt);
+    });
+}
+
 // ---- multi-device gather ----
 
 int xn_frame_gather(xn_ctx* const* ctxs, int n, uint32_t* host_dst, xn_rect* enclosing_out) {

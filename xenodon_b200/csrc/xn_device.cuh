@@ -125,6 +125,7 @@ struct FrameParams {
     uint32_t* pool;
     uint32_t pool_total, pool_blocks_x;
 
+    uint32_t* touch_bits;           // touch pass only: one bit per voxel (x-major linear order) fetched
     uint32_t* steps_out;            // stats pass only
     unsigned long long* bytes_out;  // stats pass only
 };

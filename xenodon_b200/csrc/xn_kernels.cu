@@ -588,6 +588,23 @@ struct TexFetch<true> {
     static __device__ __forceinline__ texel zero() { return make_uchar4(0, 0, 0, 0); }
 };
 
+// The instrumented pass can also record WHICH voxels a frame fetches (xn_render_touch_pass): one bit
+// per voxel of the x-major linear order, so a byte of the map is one 32-byte sector of that layout.
+template <bool STRICT, bool STATS>
+struct TexFetchS : TexFetch<STRICT> {
+    typedef typename TexFetch<STRICT>::texel texel;
+    static __device__ __forceinline__ texel fetch(const FrameParams& p, float x, float y, float z) {
+        if (STATS && p.touch_bits) {
+            const int vx = __float2int_rd(x), vy = __float2int_rd(y), vz = __float2int_rd(z);
+            if ((uint32_t)vx < p.nx && (uint32_t)vy < p.ny && (uint32_t)vz < p.nz) { // border texels are not memory
+                const uint64_t i = (uint64_t)vx + (uint64_t)p.nx * ((uint64_t)vy + (uint64_t)p.ny * (uint64_t)vz);
+                atomicOr(p.touch_bits + (i >> 5), 1u << (uint32_t)(i & 31u));
+            }
+        }
+        return TexFetch<STRICT>::fetch(p, x, y, z);
+    }
+};
+
 // emission accumulator of the texture path: strict = shader order on exact c / 255,
 // fast = fma on the texture unit's c / 255 (scaled by the emission coefficient only)
 template <bool STRICT>
@@ -615,7 +632,7 @@ struct TexAccum<true> {
 
 template <bool STATS, bool STRICT>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_TEX_MIN_BLOCKS) dda_tex_kernel(const __grid_constant__ FrameParams p) {
-    typedef TexFetch<STRICT> TF;
+    typedef TexFetchS<STRICT, STATS> TF;
     typedef typename TF::texel texel;
     uint32_t ix, iy;
     thread_pixel<true>(p, ix, iy);
@@ -864,7 +881,7 @@ __device__ __forceinline__ void dda_axis_jump(float& s, const float d, const flo
 template <bool STATS, bool STRICT>
 __global__ void __launch_bounds__(BLOCK_THREADS, XN_SKIP_MIN_BLOCKS)
     dda_skip_tex_kernel(const __grid_constant__ FrameParams p) {
-    typedef TexFetch<STRICT> TF;
+    typedef TexFetchS<STRICT, STATS> TF;
     typedef typename TF::texel texel;
     uint32_t ix, iy;
     thread_pixel<true>(p, ix, iy);

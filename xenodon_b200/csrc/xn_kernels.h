@@ -36,6 +36,8 @@ cudaError_t launch_count_black(const uint32_t* grid, uint64_t n, uint64_t stride
 // *uniform_fraction_out (nullable) = share of the grid's bricks that hold one colour
 cudaError_t build_skip_table(const uint32_t* grid, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t shift, uint32_t cap,
                              uint4** table_out, uint32_t dims_out[3], double* uniform_fraction_out, cudaStream_t stream);
+// out2[0] += bits set, out2[1] += non-zero bytes of a touch map of `words` 32-bit words
+cudaError_t launch_touch_count(const uint32_t* bits, uint64_t words, unsigned long long* out2, cudaStream_t stream);
 cudaError_t launch_stats_totals(const uint32_t* steps, const unsigned long long* bytes, uint64_t n,
                                 unsigned long long* totals, cudaStream_t stream);
 } // namespace xn

@@ -505,6 +505,29 @@ __global__ void stats_totals_kernel(const uint32_t* __restrict__ steps, const un
     }
 }
 
+// touch map -> (bits set = voxels fetched, non-zero bytes = 32-byte sectors of the linear layout fetched)
+__global__ void touch_count_kernel(const uint32_t* __restrict__ bits, uint64_t words, unsigned long long* __restrict__ out) {
+    unsigned long long voxels = 0, sectors = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = bits[i];
+        voxels += (unsigned)__popc(w);
+        sectors += ((w & 0xFFu) != 0u) + ((w & 0xFF00u) != 0u) + ((w & 0xFF0000u) != 0u) + ((w & 0xFF000000u) != 0u);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        voxels += __shfl_down_sync(0xFFFFFFFFu, voxels, o);
+        sectors += __shfl_down_sync(0xFFFFFFFFu, sectors, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (voxels) atomicAdd(out, voxels);
+        if (sectors) atomicAdd(out + 1, sectors);
+    }
+}
+cudaError_t launch_touch_count(const uint32_t* bits, uint64_t words, unsigned long long* out2, cudaStream_t stream) {
+    const unsigned blocks = (unsigned)std::min<uint64_t>((words + 255) / 256, 148u * 16u);
+    touch_count_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(bits, words, out2);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stats_totals(const uint32_t* steps, const unsigned long long* bytes, uint64_t n,
                                 unsigned long long* totals, cudaStream_t stream) {
     stats_totals_kernel<<<148 * 4, 256, 0, stream>>>(steps, bytes, n, totals);

@@ -297,8 +297,8 @@ def roofline_block(workload, traversal, kernel_name, alg_bytes, alg_steps, n_sta
                 "traffic is far below it -- see dram_frac and the ncu evidence",
     }
     if prof:
-        for k in ("dram_frac_of_measured_peak", "issue_active", "lanes_per_instruction", "l2_hit", "capture_ms",
-                  "evidence"):
+        for k in ("dram_frac_of_measured_peak", "issue_active", "lanes_per_instruction", "l2_hit", "l2_gb_per_s",
+                  "capture_ms", "capture", "evidence"):
             if k in prof:
                 block[k] = prof[k]
         if traffic is not None and "capture_ms" in prof:

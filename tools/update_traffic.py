@@ -56,6 +56,9 @@ def entry(path, note=None):
         "tex_wavefronts": round(tex, 1), "lsu_wavefronts": round(lsu, 1),
         "l1_hit": round(d.get("l1tex__t_sector_hit_rate.pct", 0.0), 1),
         "l2_hit": round(d.get("lts__t_sector_hit_rate.pct", 0.0), 1),
+        # achieved L2 rate: 32-byte sectors the L2 slices served per second of the capture
+        "l2_gb_per_s": round(d.get("lts__t_sectors.sum", 0.0) * 32 / (ms / 1e3) / 1e9, 1),
+        "l2_throughput_pct": round(d.get("lts__throughput.avg.pct_of_peak_sustained_elapsed", 0.0), 1),
         "warps_active": round(d.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0.0), 1),
         "registers": int(d.get("launch__registers_per_thread", 0)),
         "warp_instructions": round(d.get("smsp__inst_executed.sum", 0)),

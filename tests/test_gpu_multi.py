@@ -62,7 +62,7 @@ def test_interleaved_contexts_compose_the_full_frame(xb, xo):
 
 
 def test_pipelined_frame_output_and_async_frame_read(xb, xo):
-    """xn_render_download_async (double-buffered targets + copy stream) and
+    """xn_render_download_async (three device targets in rotation + copy stream) and
     xn_frame_buffer_read_async deliver the same pixels as the blocking calls."""
     g = blobby_grid(np.random.default_rng(79), 32, 32, 32)
     W, H = 160, 96
@@ -73,7 +73,7 @@ def test_pipelined_frame_output_and_async_frame_read(xb, xo):
     ctx.set_params((1, 1, 1), None, 2.0)
     cams = [CAMERAS["orbit"], CAMERAS["single"], CAMERAS["inside"], CAMERAS["axis_neg"], CAMERAS["orbit"]]
     frames = [xb.PinnedFrame(W, H) for _ in cams]
-    for cam, fr in zip(cams, frames):  # five frames in flight through two alternating targets
+    for cam, fr in zip(cams, frames):  # five frames in flight through three targets: the rotation wraps
         ctx.render_download_async("dda", cam, fr)
     ms = ctx.sync()
     assert ms > 0 and ctx.launch_count() == len(cams)

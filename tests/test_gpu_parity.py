@@ -527,3 +527,28 @@ def test_touch_pass_counts_the_voxels_a_frame_fetches(xb, xo):
             ctx.touch_pass(CAMERAS["orbit"])
     finally:
         ctx.close()
+
+
+def test_degenerate_inputs(xb, xo):
+    """The smallest inputs the formats allow: a one-voxel grid and its one-leaf octree on 1x1, 3x2 and
+    17x16 frames (a frame smaller than a block, and one a pixel wider than a block), for every
+    traversal, and a zero-area region, which renders nothing and is not an error."""
+    g = np.zeros((1, 1, 1, 4), np.uint8)
+    g[0, 0, 0] = (200, 100, 50, 255)
+    tree, _ = xb.build_octree(xb.Grid(g), chan_diff=0, type=xb.TYPE_ROPE)
+    for (w, h) in ((1, 1), (3, 2), (17, 16)):
+        _compare(xb, xo, "dda", grid=g, camera=CAMERAS["single"], output=(0, 0, w, h), display=(0, 0, w, h), emission=0.5)
+        for trav in SVO_TRAVERSALS:
+            _compare(xb, xo, trav, tree=tree, camera=CAMERAS["single"], output=(0, 0, w, h), display=(0, 0, w, h),
+                     emission=0.5)
+    ctx = xb.Context(0)
+    try:
+        ctx.upload_grid(xb.Grid(g))
+        ctx.set_target((5, 5, 0, 0), (0, 0, 16, 16))
+        ctx.set_params((1, 1, 1), None, 1.0)
+        ctx.render("dda", CAMERAS["single"])
+        ctx.sync()
+        assert ctx.download().shape[:2] == (0, 0)
+        assert ctx.stats_pass("dda", CAMERAS["single"], per_ray=False)[2] == (0, 0)
+    finally:
+        ctx.close()

@@ -303,6 +303,12 @@ def roofline_block(workload, traversal, kernel_name, alg_bytes, alg_steps, n_sta
                 block[k] = prof[k]
         if traffic is not None and "capture_ms" in prof:
             block["dram_frac"] = round(traffic / (prof["capture_ms"] / 1e3) / 1e9 / peak, 4)
+        # how close the unit named by `bound` is to its own ceiling in that capture
+        near = {"issue": max(prof.get("issue_active", 0.0), prof.get("pipe_alu", 0.0), prof.get("pipe_fma", 0.0)),
+                "tex": prof.get("tex_wavefronts", 0.0), "lsu": prof.get("lsu_wavefronts", 0.0),
+                "hbm": 100.0 * prof.get("dram_frac_of_measured_peak", 0.0)}.get(block["bound"])
+        if near is not None:
+            block["bound_frac"] = round(near / 100.0, 3)
     return block
 
 
